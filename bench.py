@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ParticleSfM hot paths.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one global bundle adjustment (HP2) of the BASELINE.json target workload
+— F=200 frames x P=500k trajectories x 12 observations/track, synthetic (SURVEY.md §8d
+"target config", seed 5) — from the perturbed start to the reference's termination
+criteria (GlobalBundleAdjustment options, controllers/global_mapper.cc:41-71, pass B:
+rotations + focal length refined).
+
+`value`  = observations / second of solve = M / t_step, problem resident in HBM
+           (observations, structure uploaded once; the state is re-set every step).
+`e2e`    = same metric through psfm_ba_solve() on HOST buffers: flattening, H2D of
+           observations/state, solve, D2H of the result inside the timed region.
+The line also carries the HP1 number (trajectory optimiser, pts/s) under "traj_opt".
+
+`--impl reference` times the CPU oracle port (the reference's algorithm choices: exact
+Schur, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(num_images=200, num_points=500_000, track_len=12, seed=5)
+CPU_SAMPLE_POINTS = 50_000
+TRAJ = dict(num=111_616, height=436, width=1024, seed=1)   # Sintel alley_1 @ sample_ratio 2
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        # samples taken under load = upper half of the observed clocks
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def global_pass_b_options(abi, lib, solver):
+    o = abi.BAOptions()
+    lib.psfm_ba_global_options(C.byref(o))
+    o.refine_rotation = 1          # AdjustGlobalBundle(force_update_rotation=true), controllers/global_mapper.cc:219-224
+    o.refine_focal_length = 1
+    o.minimizer_progress_to_stdout = 0
+    o.print_summary = 0
+    o.linear_solver = solver
+    return o
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port (exact Schur = what the reference picks for F <= 1000,
+    bundle_adjustment.cc:276-286) on all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import oracle
+    from particlesfm_b200 import synthetic as syn, _abi
+    w = dict(WORKLOAD)
+    w["num_points"] = args.cpu_points
+    prob, _ = syn.make_ba_problem(**w)
+    o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
+    o.linear_solver = _abi.SOLVER_AUTO
+    M = prob.num_observations
+    times, iters = [], 0
+    for k in range(args.warmup + args.steps):
+        p = prob.copy()
+        t0 = time.perf_counter()
+        s = oracle.ba_solve(p, o)
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            times.append(dt)
+            iters += s.num_iterations
+    total = sum(times)
+    val = M * len(times) / total
+    cores = oracle.num_threads()
+    sample = f"F={w['num_images']} P={w['num_points']} L={w['track_len']} seed={w['seed']} (M={M}; 1/{WORKLOAD['num_points'] // w['num_points']} of the points)"
+    line = {
+        "impl": "reference", "metric": "global_ba_observations_per_sec", "value": val, "unit": "observations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "global BA pass B, 200 frames x 500k trajectories x 12 obs (bounded sample: " + sample + ")",
+                   "linear_solver": "exact Schur + dense Cholesky (reference rule for <= 1000 images)"},
+        "lm_iterations_per_step": iters / len(times),
+        "obs_iterations_per_sec": M * iters / total,
+        "cpu_baseline": {"value": val, "unit": "observations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=WORKLOAD["num_points"], help="trajectories of the BA workload")
+    ap.add_argument("--cpu-points", type=int, default=CPU_SAMPLE_POINTS)
+    ap.add_argument("--solver", default="iterative", choices=["iterative", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traj", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    from particlesfm_b200 import _abi, _lib, ba, synthetic as syn, traj
+    lib = _lib.lib()
+    if lib.psfm_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    _lib.check(lib.psfm_set_device(local_rank), "psfm_set_device")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = (C.c_uint8 * _abi.NCCL_UNIQUE_ID_BYTES)()
+        if rank == 0:
+            _lib.check(lib.psfm_dist_get_unique_id(uid), "psfm_dist_get_unique_id")
+        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        uid = (C.c_uint8 * _abi.NCCL_UNIQUE_ID_BYTES)(*t.cpu().tolist())
+        _lib.check(lib.psfm_dist_init(uid, rank, world), "psfm_dist_init")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = dict(WORKLOAD)
+    w["num_points"] = args.points
+    full, truth = syn.make_ba_problem(**w)
+    M_total = full.num_observations
+    prob = full.shard(rank, world)
+    solver_mode = _abi.SOLVER_ITERATIVE_SCHUR if args.solver == "iterative" else _abi.SOLVER_EXACT_SCHUR
+    o = global_pass_b_options(_abi, lib, solver_mode)
+    init = (full.qvec.copy(), full.tvec.copy(), full.xyz.copy(), full.cam_params.copy())
+
+    # ---------------- device-resident arm ----------------
+    S = ba.ResidentSolver(prob)
+    summaries = []
+
+    def step():
+        S.set_state(*init)
+        return S.run(o)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.psfm_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        summaries.append(step())          # psfm_ba_run synchronises its stream before returning
+    t_local = time.perf_counter() - t0
+    barrier()
+    t_total = max_over_ranks(t_local)
+    launches = lib.psfm_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = 1e3 * t_total / args.steps
+    value = M_total * args.steps / t_total
+    s_last = summaries[-1]
+    iters = sum(s.num_iterations for s in summaries) / len(summaries)
+    lin_its = sum(s.num_linear_iterations for s in summaries) / len(summaries)
+    S.get_state()
+    ate = syn.umeyama_ate(syn.camera_centres(prob.qvec, prob.tvec), truth["centres"])
+
+    # ---------------- roofline of the dominant kernel (live CUDA events) ----------------
+    peak, peak_src = read_peaks()
+    M_local = prob.num_observations
+    L = w["track_len"]
+    sp_bytes = (96 + 48 + 16 + 8 + 48.0 / L) * M_local          # implicit S*p, SURVEY.md §8d (+16 B focal column)
+    lin_bytes = (24 + 176 + 96.0 / L) * M_local                 # Jacobian sweep, pass B
+    n_sp = sum(s.num_schur_products for s in summaries)
+    n_lin = sum(s.num_linearize for s in summaries)
+    sp_ms = sum(s.schur_product_ms for s in summaries) / max(n_sp, 1)
+    lin_ms = sum(s.linearize_ms for s in summaries) / max(n_lin, 1)
+    sp_gbs = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
+    lin_gbs = lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
+    roofline = {"kernel": "k_schur_product (implicit S*p, one per PCG iteration)", "bound": "hbm", "achieved": sp_gbs,
+                "peak": peak, "unit": "GB/s", "frac": sp_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sp_bytes, "avg_launch_ms": sp_ms, "launches": n_sp,
+                "share_of_step": sum(s.schur_product_ms for s in summaries) / (1e3 * t_local)}
+    roofline_lin = {"kernel": "k_linearize (Jacobian sweep)", "bound": "hbm", "achieved": lin_gbs, "peak": peak,
+                    "unit": "GB/s", "frac": lin_gbs / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": lin_bytes, "avg_launch_ms": lin_ms, "launches": n_lin}
+    S.close()
+
+    # ---------------- end to end through the C ABI on host buffers ----------------
+    e2e_times = []
+    for k in range(1 + args.steps):
+        p = prob.copy()
+        p.qvec[:], p.tvec[:], p.xyz[:], p.cam_params[:] = init
+        barrier()
+        t0 = time.perf_counter()
+        ba.solve_problem(p, o)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if k >= 1:
+            e2e_times.append(dt)
+    e2e_val = M_total * len(e2e_times) / sum(e2e_times)
+    state_bytes = 8 * (full.qvec.size + full.tvec.size + full.cam_params.size) + 8 * 3 * np.unique(prob.obs_point).size
+    h2d = prob.obs_xy.nbytes + prob.obs_image.nbytes + prob.obs_point.nbytes + 2 * prob.num_observations + 4 * prob.num_observations + state_bytes
+    d2h = state_bytes
+
+    line = {
+        "metric": "global_ba_observations_per_sec", "value": value, "unit": "observations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"global BA pass B (rotation+translation+focal+points), F={w['num_images']} frames x "
+                               f"P={w['num_points']} trajectories x L={L} obs/track, M={M_total} observations, seed {w['seed']}",
+                   "options": "GlobalBundleAdjustment (SoftL1, f_tol 1e-6, g_tol 1, p_tol 1e-8, <=50 LM its)",
+                   "linear_solver": "PCG on the reduced camera system, Schur-Jacobi, eta=0.1, <=100 its (Ceres ITERATIVE_SCHUR semantics)"
+                   if args.solver == "iterative" else "PCG to |r|<=1e-10|b| (exact-step mode)",
+                   "parallelism": f"points sharded over {world} GPU(s), one NCCL all-reduce per PCG step",
+                   "l2": "working set (J = 1.1 GB/6M obs) is larger than the 126 MB L2; no flush needed"},
+        "lm_iterations_per_step": iters, "pcg_iterations_per_step": lin_its,
+        "obs_iterations_per_sec": M_total * sum(s.num_iterations for s in summaries) / t_total,
+        "device_ms_per_step": sum(s.device_ms for s in summaries) / len(summaries),
+        "final_cost": s_last.final_cost, "initial_cost": s_last.initial_cost, "termination": s_last.termination,
+        "ate_vs_truth": ate,
+        "e2e": {"value": e2e_val, "unit": "observations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline, "roofline_linearize": roofline_lin,
+    }
+
+    # ---------------- HP1: trajectory optimiser, pts/s (rank 0, N = 1 shape) ----------------
+    if rank == 0 and not args.no_traj:
+        uv12, r1, r2, sc, f12 = syn.make_traj_inputs(TRAJ["num"], TRAJ["height"], TRAJ["width"], seed=TRAJ["seed"])
+        n = uv12.shape[0]
+        ts, dev_ms = [], []
+        for k in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out, ssum = traj.optimize_location(uv12, r1, r2, sc, f12, n, TRAJ["width"], TRAJ["height"], return_summary=True)
+            if k >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+                dev_ms.append(ssum.solve_ms)
+        traj_bytes = 104.0 * n + 8.0 * TRAJ["height"] * TRAJ["width"]
+        line["traj_opt"] = {"metric": "traj_opt_points_per_sec", "value_e2e": n / statistics.mean(ts),
+                            "value_device": n / (statistics.mean(dev_ms) * 1e-3), "unit": "trajectories/s", "n": n,
+                            "iterations": ssum.num_iterations, "workload": "Sintel alley_1 shape 1024x436, sample_ratio 2",
+                            "roofline": {"bound": "hbm (latency-bound by design)", "achieved": traj_bytes / (statistics.mean(dev_ms) * 1e-3) / 1e9,
+                                         "peak": peak, "unit": "GB/s", "frac": traj_bytes / (statistics.mean(dev_ms) * 1e-3) / 1e9 / peak}}
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        wc = dict(WORKLOAD)
+        wc["num_points"] = args.cpu_points
+        pc, _ = syn.make_ba_problem(**wc)
+        oc = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
+        oc.linear_solver = _abi.SOLVER_AUTO
+        t0 = time.perf_counter()
+        sc_ = oracle.ba_solve(pc, oc)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": pc.num_observations / dt, "unit": "observations/s", "cores": oracle.num_threads(),
+                                "kind": "port", "lm_iterations": sc_.num_iterations,
+                                "sample": f"F={wc['num_images']} P={wc['num_points']} L={wc['track_len']} seed={wc['seed']} "
+                                          f"(M={pc.num_observations}), exact Schur + dense Cholesky, one solve to convergence ({dt:.1f} s)"}
+        if not args.no_traj:
+            t0 = time.perf_counter()
+            _, so = oracle.traj_optimize(uv12, r1, r2, sc, f12, num_threads=8)
+            line["traj_opt"]["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "trajectories/s", "cores": 8,
+                                                "kind": "port", "sample": "same call, 8 threads (trajectory_optimize.cpp:79)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        lib.psfm_dist_finalize()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -255,6 +255,13 @@ void psfm_ba_destroy(psfm_ba_solver* s);
 int psfm_ba_evaluate(psfm_ba_solver* s, const psfm_ba_options* opts, double* cost,
                      double* residuals, double* gradient_cam, double* gradient_pts);
 
+/* One linear solve (iteration-0 linearisation + Jacobi scaling, LM diagonal from
+   `radius`, Schur elimination, PCG, back-substitution) without moving the state: writes
+   the step in the scaled tangent space, camera slots [6F+3C] and points [3P].  Used by
+   the parity tests to compare the PCG step with the oracle's Cholesky step. */
+int psfm_ba_linear_step(psfm_ba_solver* s, const psfm_ba_options* opts, double radius,
+                        double* step_cam, double* step_pts, int32_t* num_linear_iterations);
+
 /* ------------------------------------------------------------------------- */
 /* Multi-GPU (HP2): points sharded across ranks, one all-reduce of the         */
 /* camera-side vector per PCG step.                            */

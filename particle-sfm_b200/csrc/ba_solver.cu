@@ -1,0 +1,962 @@
+// ba_solver.cu — host side of HP2: problem flattening/tiling, the Levenberg-Marquardt
+// trust-region loop (Ceres 2.0.0 TrustRegionMinimizer + LevenbergMarquardtStrategy
+// semantics), PCG on the reduced camera system, and the
+// C ABI of include/psfm_b200.h.
+//
+// Drop-in target: colmap::BundleAdjuster::Solve
+//   (reference sfm/gmapper/src/optim/bundle_adjustment.cc:259-320), problem assembly
+//   rules from :326-447 / :500-544, solver selection rule :276-286, option policy
+//   controllers/global_mapper.cc:41-71.
+// There is no CPU path: every numeric step below is a kernel launch.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
+#include "ba_small_kernels.cuh"
+#include "dist.cuh"
+
+namespace psfm {
+namespace ba {
+
+struct EventPool {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      PSFM_CUDA(cudaEventCreate(&e));
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  void reset() { used = 0; }
+  ~EventPool() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
+struct HostScalars {   // pinned
+  double lin_cost;
+  double gmax;
+  double prep_fail;
+  double step[4];      // sum m(r+m/2), |dX|^2, |Xc|^2, candidate cost
+  double rep[2];       // |dcam|^2, |cam_c|^2
+  double x2;
+  PcgState pcg;
+};
+
+}  // namespace ba
+}  // namespace psfm
+
+using namespace psfm;
+using namespace psfm::ba;
+
+struct psfm_ba_solver {
+  int F = 0, P_total = 0, P = 0, M = 0, C = 0, NS = 0, NB = 0, T = 0, nseg = 0, tile = 256, maxL = 0;
+  // host structure / config
+  std::vector<int> pt_orig;      // internal point -> caller's point id
+  std::vector<int> obs_orig;     // sorted observation -> caller's observation index
+  std::vector<int> image_camera;
+  std::vector<unsigned char> pose_constant, tvec_mask, camera_constant, img_has_obs, cam_has_obs;
+  // host state (caller layout)
+  std::vector<double> h_qvec, h_tvec, h_xyz, h_K;
+  // device structure
+  DBuf<int> d_tile_start, d_tile_pt, d_pt_ptr, d_obs_img, d_obs_pt, d_cseg_ptr, d_cseg_img, d_img_cam;
+  DBuf<unsigned short> d_tile_perm, d_cseg_off;
+  DBuf<double2> d_obs_xy;
+  DBuf<unsigned char> d_active;
+  // device state
+  DBuf<double> d_pose[2], d_X[2], d_K[2];
+  int cur = 0;
+  // linearisation
+  DBuf<double> d_r, d_jc, d_jp, d_jk, d_hpp, d_gp, d_wk, d_hinv, d_w, d_scale_c, d_scale_p;
+  size_t jc_rows = 0, jk_rows = 0;
+  // reduced system / PCG
+  DBuf<double> d_lin, d_prep, d_step, d_rep, d_gmax, d_x2, d_Dc2, d_Minv, d_rhs, d_x, d_rv, d_p, d_z, d_y, d_zero;
+  DBuf<PcgState> d_pcg;
+  HostScalars* hs = nullptr;
+  cudaStream_t stream = nullptr;
+  EventPool events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lin, ev_sp;
+
+  TileCtx tc() const {
+    TileCtx t;
+    t.tile_start = d_tile_start.p; t.tile_pt = d_tile_pt.p; t.pt_ptr = d_pt_ptr.p;
+    t.obs_img = d_obs_img.p; t.obs_pt = d_obs_pt.p; t.obs_xy = d_obs_xy.p;
+    t.tile_perm = d_tile_perm.p; t.cseg_ptr = d_cseg_ptr.p; t.cseg_img = d_cseg_img.p;
+    t.cseg_off = d_cseg_off.p; t.img_cam = d_img_cam.p;
+    t.F = F; t.P = P; t.M = M; t.C = C; t.T = T;
+    return t;
+  }
+  ~psfm_ba_solver() {
+    if (hs) cudaFreeHost(hs);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- structure
+
+int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
+  const int F = pb->num_images, Pt = pb->num_points, M = pb->num_observations, C = pb->num_cameras;
+  if (F <= 0 || C <= 0 || Pt < 0 || M < 0) { set_error("psfm_ba_create: bad sizes"); return PSFM_ERR_INVALID; }
+  S->F = F; S->P_total = Pt; S->M = M; S->C = C; S->NS = 6 * F + 3 * C; S->NB = 2 * F + C;
+  S->image_camera.assign(pb->image_camera, pb->image_camera + F);
+  for (int i = 0; i < F; ++i)
+    if (S->image_camera[i] < 0 || S->image_camera[i] >= C) { set_error("image_camera out of range"); return PSFM_ERR_INVALID; }
+  S->pose_constant.assign(F, 0); S->tvec_mask.assign(F, 0); S->camera_constant.assign(C, 0);
+  if (pb->pose_constant) S->pose_constant.assign(pb->pose_constant, pb->pose_constant + F);
+  if (pb->tvec_constant_mask) S->tvec_mask.assign(pb->tvec_constant_mask, pb->tvec_constant_mask + F);
+  if (pb->camera_constant) S->camera_constant.assign(pb->camera_constant, pb->camera_constant + C);
+  S->img_has_obs.assign(F, 0); S->cam_has_obs.assign(C, 0);
+
+  // points: observation counts and first image
+  std::vector<int> cnt(Pt, 0), min_img(Pt, F);
+  for (int i = 0; i < M; ++i) {
+    const int im = pb->obs_image[i], pt = pb->obs_point[i];
+    if (im < 0 || im >= F || pt < 0 || pt >= Pt) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
+    cnt[pt]++;
+    if (im < min_img[pt]) min_img[pt] = im;
+    S->img_has_obs[im] = 1;
+    S->cam_has_obs[S->image_camera[im]] = 1;
+  }
+  // internal point order: observed points by (first image, id) — keeps the image window
+  // of a tile narrow for video tracks (few image segments per tile)
+  std::vector<int> bucket(F + 2, 0);
+  int P = 0;
+  for (int p = 0; p < Pt; ++p) if (cnt[p] > 0) { bucket[min_img[p] + 1]++; ++P; }
+  for (int f = 0; f < F; ++f) bucket[f + 1] += bucket[f];
+  S->P = P;
+  S->pt_orig.assign(P, 0);
+  std::vector<int> pt_new(Pt, -1);
+  for (int p = 0; p < Pt; ++p) if (cnt[p] > 0) { const int id = bucket[min_img[p]]++; S->pt_orig[id] = p; pt_new[p] = id; }
+  std::vector<int> pt_ptr(P + 1, 0);
+  int maxL = 0;
+  for (int id = 0; id < P; ++id) { pt_ptr[id + 1] = pt_ptr[id] + cnt[S->pt_orig[id]]; maxL = std::max(maxL, cnt[S->pt_orig[id]]); }
+  S->maxL = maxL;
+  if (maxL > 1024) { set_error("a track with more than 1024 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
+  S->tile = maxL <= 256 ? 256 : (maxL <= 512 ? 512 : 1024);
+  // sort observations by (internal point, image): counting sort by image, then stable by point
+  std::vector<int> by_img(M);
+  {
+    std::vector<int> ib(F + 1, 0);
+    for (int i = 0; i < M; ++i) ib[pb->obs_image[i] + 1]++;
+    for (int f = 0; f < F; ++f) ib[f + 1] += ib[f];
+    for (int i = 0; i < M; ++i) by_img[ib[pb->obs_image[i]]++] = i;
+  }
+  S->obs_orig.assign(M, 0);
+  {
+    std::vector<int> fill(pt_ptr.begin(), pt_ptr.end() - 1);
+    for (int j = 0; j < M; ++j) { const int i = by_img[j]; S->obs_orig[fill[pt_new[pb->obs_point[i]]]++] = i; }
+  }
+  std::vector<int> obs_img(M), obs_pt(M);
+  std::vector<double2> obs_xy(M);
+  for (int j = 0; j < M; ++j) {
+    const int i = S->obs_orig[j];
+    obs_img[j] = pb->obs_image[i];
+    obs_pt[j] = pt_new[pb->obs_point[i]];
+    obs_xy[j] = make_double2(pb->obs_xy[2 * (size_t)i], pb->obs_xy[2 * (size_t)i + 1]);
+  }
+  // tiles: whole points, <= tile observations
+  const int TILE = S->tile;
+  std::vector<int> tile_start, tile_pt;
+  tile_start.push_back(0); tile_pt.push_back(0);
+  {
+    int cur = 0;
+    for (int id = 0; id < P; ++id) {
+      const int L = pt_ptr[id + 1] - pt_ptr[id];
+      if (cur + L > TILE) { tile_start.push_back(pt_ptr[id]); tile_pt.push_back(id); cur = 0; }
+      cur += L;
+    }
+    if (P > 0) { tile_start.push_back(M); tile_pt.push_back(P); }
+  }
+  const int T = (int)tile_start.size() - 1;
+  S->T = T;
+  // per tile: image order + segments
+  std::vector<unsigned short> tile_perm(M), cseg_off;
+  std::vector<int> cseg_ptr(T + 1, 0), cseg_img;
+  cseg_off.reserve(M / 4 + 16); cseg_img.reserve(M / 4 + 16);
+  {
+    std::vector<int> cntf(F + 1, 0);
+    for (int t = 0; t < T; ++t) {
+      const int b = tile_start[t], n = tile_start[t + 1] - b;
+      int lo = F, hi = -1;
+      for (int e = 0; e < n; ++e) { const int im = obs_img[b + e]; lo = std::min(lo, im); hi = std::max(hi, im); cntf[im]++; }
+      int run = 0;
+      for (int f = lo; f <= hi; ++f) {
+        const int c = cntf[f];
+        if (c > 0) { cseg_img.push_back(f); cseg_off.push_back((unsigned short)run); }
+        cntf[f] = run;
+        run += c;
+      }
+      for (int e = 0; e < n; ++e) tile_perm[b + cntf[obs_img[b + e]]++] = (unsigned short)e;
+      for (int f = lo; f <= hi; ++f) cntf[f] = 0;
+      cseg_ptr[t + 1] = (int)cseg_img.size();
+    }
+  }
+  S->nseg = (int)cseg_img.size();
+  // upload
+  cudaStream_t st = S->stream;
+  S->d_tile_start.alloc(T + 1); S->d_tile_start.upload(tile_start.data(), T + 1, st);
+  S->d_tile_pt.alloc(T + 1); S->d_tile_pt.upload(tile_pt.data(), T + 1, st);
+  S->d_pt_ptr.alloc(P + 1); S->d_pt_ptr.upload(pt_ptr.data(), P + 1, st);
+  S->d_obs_img.alloc(M); S->d_obs_img.upload(obs_img.data(), M, st);
+  S->d_obs_pt.alloc(M); S->d_obs_pt.upload(obs_pt.data(), M, st);
+  S->d_obs_xy.alloc(M); S->d_obs_xy.upload(obs_xy.data(), M, st);
+  S->d_tile_perm.alloc(M); S->d_tile_perm.upload(tile_perm.data(), M, st);
+  S->d_cseg_ptr.alloc(T + 1); S->d_cseg_ptr.upload(cseg_ptr.data(), T + 1, st);
+  S->d_cseg_img.alloc(S->nseg); S->d_cseg_img.upload(cseg_img.data(), S->nseg, st);
+  S->d_cseg_off.alloc(S->nseg); S->d_cseg_off.upload(cseg_off.data(), S->nseg, st);
+  S->d_img_cam.alloc(F); S->d_img_cam.upload(S->image_camera.data(), F, st);
+  PSFM_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+  return PSFM_OK;
+}
+
+void alloc_work(psfm_ba_solver* S) {
+  const size_t M = S->M, P = S->P, F = S->F, C = S->C, NS = S->NS;
+  S->d_active.alloc(NS);
+  for (int k = 0; k < 2; ++k) { S->d_pose[k].alloc(8 * F); S->d_X[k].alloc(3 * P); S->d_K[k].alloc(3 * C); }
+  S->d_r.alloc(2 * M); S->d_jp.alloc(6 * M);
+  S->jc_rows = 0; S->jk_rows = 0;   // d_jc / d_jk sized on first run (depends on options)
+  S->d_hpp.alloc(6 * P); S->d_gp.alloc(3 * P); S->d_wk.alloc(9 * P); S->d_hinv.alloc(6 * P); S->d_w.alloc(3 * P);
+  S->d_scale_c.alloc(NS); S->d_scale_p.alloc(3 * P);
+  S->d_lin.alloc(F * NVL + C * NVI + 1);
+  S->d_prep.alloc(F * NVL + C * NVI + 1);
+  S->d_step.alloc(4); S->d_rep.alloc(2); S->d_gmax.alloc(1); S->d_x2.alloc(1);
+  S->d_Dc2.alloc(NS); S->d_Minv.alloc(9 * (size_t)S->NB); S->d_rhs.alloc(NS);
+  S->d_x.alloc(NS); S->d_rv.alloc(NS); S->d_p.alloc(NS); S->d_z.alloc(NS); S->d_y.alloc(NS); S->d_zero.alloc(NS);
+  S->d_zero.zero(S->stream);
+  S->d_pcg.alloc(1);
+  PSFM_CUDA(cudaMallocHost((void**)&S->hs, sizeof(HostScalars)));
+  memset(S->hs, 0, sizeof(HostScalars));
+}
+
+// ---------------------------------------------------------------- kernel dispatch
+
+#define PSFM_TILE_LAUNCH(KERNEL, NV, S, ROT, ARGS)                                                         \
+  do {                                                                                                     \
+    const TileCtx _tc = (S)->tc();                                                                         \
+    if ((S)->T > 0) {                                                                                      \
+      auto _go = [&](auto tile_c, auto rot_c) {                                                            \
+        constexpr int TL = decltype(tile_c)::value;                                                        \
+        constexpr bool RT = decltype(rot_c)::value;                                                        \
+        const size_t smem = TileSmem<TL, NV>::bytes();                                                     \
+        static bool attr_set = false;                                                                      \
+        if (!attr_set) {                                                                                   \
+          PSFM_CUDA(cudaFuncSetAttribute(KERNEL<TL, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         (int)smem));                                                      \
+          attr_set = true;                                                                                 \
+        }                                                                                                  \
+        KERNEL<TL, RT><<<(S)->T, TL, smem, (S)->stream>>>(_tc, ARGS);                                       \
+      };                                                                                                   \
+      using std::integral_constant;                                                                        \
+      if ((S)->tile == 256) { if (ROT) _go(integral_constant<int, 256>{}, std::true_type{}); else _go(integral_constant<int, 256>{}, std::false_type{}); } \
+      else if ((S)->tile == 512) { if (ROT) _go(integral_constant<int, 512>{}, std::true_type{}); else _go(integral_constant<int, 512>{}, std::false_type{}); } \
+      else { if (ROT) _go(integral_constant<int, 1024>{}, std::true_type{}); else _go(integral_constant<int, 1024>{}, std::false_type{}); } \
+      PSFM_LAUNCH_CHECK();                                                                                 \
+    }                                                                                                      \
+  } while (0)
+
+struct RunCfg {
+  psfm_ba_options o;
+  bool rot = false;
+  int intr = 0;
+  int solver = 0;
+  std::vector<unsigned char> active;
+  int num_effective_parameters = 0;
+};
+
+int resolve_cfg(psfm_ba_solver* S, const psfm_ba_options* opts, RunCfg& c) {
+  if (opts) c.o = *opts; else psfm_ba_default_options(&c.o);
+  const psfm_ba_options& o = c.o;
+  const int F = S->F, C = S->C;
+  c.active.assign(S->NS, 0);
+  bool any_rot = false;
+  for (int i = 0; i < F; ++i) {
+    const bool constant_pose = !o.refine_extrinsics || S->pose_constant[i];   // bundle_adjustment.cc:361-362
+    if (!S->img_has_obs[i] || constant_pose) continue;
+    for (int k = 0; k < 3; ++k) {
+      c.active[6 * i + k] = o.refine_rotation ? 1 : 0;                        // :429-431
+      c.active[6 * i + 3 + k] = ((S->tvec_mask[i] >> k) & 1) ? 0 : 1;         // :432-444
+    }
+    any_rot |= o.refine_rotation != 0;
+  }
+  // ParameterizeCameras (:500-544); SIMPLE_PINHOLE: focal {0}, principal point {1,2}, no extra
+  const bool constant_camera = !o.refine_focal_length && !o.refine_principal_point && !o.refine_extra_params;
+  bool any_f = false, any_pp = false;
+  for (int cc = 0; cc < C; ++cc) {
+    if (!S->cam_has_obs[cc] || constant_camera || S->camera_constant[cc]) continue;
+    c.active[6 * F + 3 * cc] = o.refine_focal_length ? 1 : 0;
+    c.active[6 * F + 3 * cc + 1] = c.active[6 * F + 3 * cc + 2] = o.refine_principal_point ? 1 : 0;
+    any_f |= o.refine_focal_length != 0;
+    any_pp |= o.refine_principal_point != 0;
+  }
+  c.rot = any_rot;
+  c.intr = any_pp ? 3 : (any_f ? 1 : 0);
+  if (c.intr > 0 && C > 1) {
+    set_error("refining intrinsics is supported for a single shared camera (the pipeline's single_camera=1)");
+    return PSFM_ERR_UNSUPPORTED;
+  }
+  c.solver = o.linear_solver;
+  if (c.solver == PSFM_BA_SOLVER_AUTO)   // bundle_adjustment.cc:276-286
+    c.solver = (F <= 1000) ? PSFM_BA_SOLVER_EXACT_SCHUR : PSFM_BA_SOLVER_ITERATIVE_SCHUR;
+  int np = 0;
+  for (unsigned char a : c.active) np += a;
+  c.num_effective_parameters = np;   // + 3 per observed point, added by the caller (all ranks)
+  return PSFM_OK;
+}
+
+void upload_state(psfm_ba_solver* S) {
+  const int F = S->F, P = S->P;
+  std::vector<double> pose(8 * (size_t)F, 0.0), X(3 * (size_t)P);
+  for (int i = 0; i < F; ++i) {
+    // image.NormalizeQvec() — bundle_adjustment.cc:355
+    double* q = &S->h_qvec[4 * (size_t)i];
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n == 0.0) { q[0] = 1.0; q[1] = q[2] = q[3] = 0.0; }
+    else for (int k = 0; k < 4; ++k) q[k] /= n;
+    for (int k = 0; k < 4; ++k) pose[8 * (size_t)i + k] = q[k];
+    for (int k = 0; k < 3; ++k) pose[8 * (size_t)i + 4 + k] = S->h_tvec[3 * (size_t)i + k];
+  }
+  for (int id = 0; id < P; ++id)
+    for (int k = 0; k < 3; ++k) X[3 * (size_t)id + k] = S->h_xyz[3 * (size_t)S->pt_orig[id] + k];
+  S->cur = 0;
+  S->d_pose[0].upload(pose.data(), pose.size(), S->stream);
+  S->d_X[0].upload(X.data(), X.size(), S->stream);
+  S->d_K[0].upload(S->h_K.data(), S->h_K.size(), S->stream);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+}
+
+void download_state(psfm_ba_solver* S) {
+  const int F = S->F, P = S->P;
+  std::vector<double> pose(8 * (size_t)F), X(3 * (size_t)P);
+  PSFM_CUDA(cudaMemcpyAsync(pose.data(), S->d_pose[S->cur].p, pose.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  if (P) PSFM_CUDA(cudaMemcpyAsync(X.data(), S->d_X[S->cur].p, X.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  PSFM_CUDA(cudaMemcpyAsync(S->h_K.data(), S->d_K[S->cur].p, S->h_K.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  for (int i = 0; i < F; ++i) {
+    for (int k = 0; k < 4; ++k) S->h_qvec[4 * (size_t)i + k] = pose[8 * (size_t)i + k];
+    for (int k = 0; k < 3; ++k) S->h_tvec[3 * (size_t)i + k] = pose[8 * (size_t)i + 4 + k];
+  }
+  for (int id = 0; id < P; ++id)
+    for (int k = 0; k < 3; ++k) S->h_xyz[3 * (size_t)S->pt_orig[id] + k] = X[3 * (size_t)id + k];
+}
+
+Jac jac_of(psfm_ba_solver* S) {
+  Jac J;
+  J.r = S->d_r.p; J.jc = S->d_jc.p; J.jp = S->d_jp.p; J.jk = S->d_jk.p;
+  return J;
+}
+
+void ensure_jac(psfm_ba_solver* S, const RunCfg& c) {
+  const size_t rows = c.rot ? 12 : 6, krows = c.intr == 3 ? 4 : (c.intr == 1 ? 2 : 0);
+  if (S->jc_rows < rows || !S->d_jc.p) { S->d_jc.alloc(rows * (size_t)S->M); S->jc_rows = rows; }
+  if (S->jk_rows < krows || !S->d_jk.p) { S->d_jk.alloc(std::max<size_t>(krows, 1) * (size_t)S->M); S->jk_rows = krows; }
+}
+
+template <typename T>
+void d2h(psfm_ba_solver* S, T* dst, const T* src, size_t n) {
+  PSFM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, S->stream));
+}
+
+// Jacobian sweep at the current state (r, J, E'E, E'r, F'F blocks, F'r, cost)
+void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
+  S->d_lin.zero(S->stream);
+  LinArgs a;
+  a.pose = S->d_pose[S->cur].p; a.X = S->d_X[S->cur].p; a.K = S->d_K[S->cur].p;
+  a.scale_c = S->d_scale_c.p; a.scale_p = S->d_scale_p.p;
+  a.loss.type = c.o.loss_function_type; a.loss.a = c.o.loss_function_scale;
+  a.intr = c.intr;
+  a.J = jac_of(S);
+  a.hpp = S->d_hpp.p; a.gp = S->d_gp.p; a.wk = S->d_wk.p;
+  a.acc_cam = S->d_lin.p; a.acc_intr = S->d_lin.p + (size_t)S->F * NVL;
+  a.acc_cost = S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
+  PSFM_TILE_LAUNCH(k_linearize, 18, S, c.rot, a);
+  if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_lin.push_back({e0, e1}); }
+  dist::allreduce_sum(S->d_lin.p, S->d_lin.n, S->stream);
+}
+
+// per-point (E'E + D^2)^-1, its product with E'r, the points' share of gradient_max_norm
+void do_point_blocks(psfm_ba_solver* S, const RunCfg& c, double radius) {
+  if (S->P == 0) return;
+  PtsArgs a;
+  a.hpp = S->d_hpp.p; a.gp = S->d_gp.p; a.wk = S->d_wk.p; a.scale_p = S->d_scale_p.p;
+  a.radius = radius; a.min_diag = c.o.min_lm_diagonal; a.max_diag = c.o.max_lm_diagonal;
+  a.intr = c.intr; a.P = S->P;
+  a.hinv = S->d_hinv.p; a.w = S->d_w.p;
+  a.acc_intr = S->d_prep.p + (size_t)S->F * NVL;
+  a.acc_fail = S->d_prep.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
+  a.gmax = S->d_gmax.p;
+  k_point_blocks<<<(S->P + 255) / 256, 256, 0, S->stream>>>(a);
+  PSFM_LAUNCH_CHECK();
+}
+
+void do_cam_gmax(psfm_ba_solver* S) {
+  const int n = S->F + S->C;
+  k_cam_gmax<<<(n + 127) / 128, 128, 0, S->stream>>>(S->d_lin.p, S->d_lin.p + (size_t)S->F * NVL, S->d_scale_c.p,
+                                                     S->d_active.p, S->d_pose[S->cur].p, S->F, S->C, S->d_gmax.p);
+  PSFM_LAUNCH_CHECK();
+}
+
+// reduced system: Schur-Jacobi blocks, rhs, LM diagonal
+void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius) {
+  S->d_prep.zero(S->stream);
+  do_point_blocks(S, c, radius);
+  PrepArgs a;
+  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.w = S->d_w.p; a.acc_cam = S->d_prep.p;
+  PSFM_TILE_LAUNCH(k_schur_prep, 18, S, c.rot, a);
+  dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
+  CamFinArgs f;
+  f.lin_cam = S->d_lin.p; f.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
+  f.prep_cam = S->d_prep.p; f.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
+  f.active = S->d_active.p; f.radius = radius; f.min_diag = c.o.min_lm_diagonal; f.max_diag = c.o.max_lm_diagonal;
+  f.F = S->F; f.C = S->C; f.Dc2 = S->d_Dc2.p; f.Minv = S->d_Minv.p; f.rhs = S->d_rhs.p;
+  k_cam_finalize<<<(S->NB + 127) / 128, 128, 0, S->stream>>>(f);
+  PSFM_LAUNCH_CHECK();
+}
+
+void do_schur_product(psfm_ba_solver* S, const RunCfg& c, const double* x, bool timed) {
+  SpArgs a;
+  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.x = x; a.y = S->d_y.p;
+  a.flag = &S->d_pcg.p->flag; a.intr = c.intr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
+  PSFM_TILE_LAUNCH(k_schur_product, 6, S, c.rot, a);
+  if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_sp.push_back({e0, e1}); }
+  dist::allreduce_sum(S->d_y.p, S->d_y.n, S->stream);
+}
+
+// ConjugateGradientsSolver::Solve on the implicit Schur complement; returns PcgFlag
+int do_pcg(psfm_ba_solver* S, const RunCfg& c, double q_tol, double r_tol, int max_it, int* iters, int* nprod) {
+  PcgArgs a;
+  a.st = S->d_pcg.p; a.b = S->d_rhs.p; a.Minv = S->d_Minv.p; a.Dc2 = S->d_Dc2.p;
+  a.x = S->d_x.p; a.r = S->d_rv.p; a.p = S->d_p.p; a.z = S->d_z.p; a.y = S->d_y.p;
+  a.NS = S->NS; a.NB = S->NB; a.F = S->F;
+  a.q_tol = q_tol; a.r_tol = r_tol; a.max_it = max_it; a.min_it = 0;
+  k_pcg_init<<<1, 1024, 0, S->stream>>>(a);
+  PSFM_LAUNCH_CHECK();
+  const int period = c.o.pcg_check_period > 0 ? c.o.pcg_check_period : 4;
+  PcgState st;
+  st.flag = PCG_RUNNING; st.it = 1;
+  for (int it = 1; it <= max_it; ++it) {
+    do_schur_product(S, c, S->d_p.p, true);
+    ++*nprod;
+    if (it % 10 != 0) {   // residual_reset_period = 10
+      k_pcg_update<<<1, 1024, 0, S->stream>>>(a, 0);
+      PSFM_LAUNCH_CHECK();
+    } else {
+      k_pcg_update<<<1, 1024, 0, S->stream>>>(a, 1);
+      PSFM_LAUNCH_CHECK();
+      do_schur_product(S, c, S->d_x.p, true);
+      ++*nprod;
+      k_pcg_update<<<1, 1024, 0, S->stream>>>(a, 2);
+      PSFM_LAUNCH_CHECK();
+    }
+    if (it % period == 0 || it == max_it) {
+      d2h(S, &S->hs->pcg, S->d_pcg.p, 1);
+      PSFM_CUDA(cudaStreamSynchronize(S->stream));
+      st = S->hs->pcg;
+      if (st.flag != PCG_RUNNING) break;
+    }
+  }
+  if (st.flag == PCG_RUNNING) {   // max_it == 0 corner
+    d2h(S, &S->hs->pcg, S->d_pcg.p, 1);
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    st = S->hs->pcg;
+  }
+  *iters = st.it;
+  return st.flag;
+}
+
+void set_masks_and_unit_scale(psfm_ba_solver* S, const RunCfg& c) {
+  S->d_active.upload(c.active.data(), c.active.size(), S->stream);
+  std::vector<double> sc(S->NS);
+  for (int k = 0; k < S->NS; ++k) sc[k] = c.active[k] ? 1.0 : 0.0;
+  S->d_scale_c.upload(sc.data(), sc.size(), S->stream);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  if (S->P) {
+    const size_t n = 3 * (size_t)S->P;
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, S->stream>>>(S->d_scale_p.p, 1.0, n);
+    PSFM_LAUNCH_CHECK();
+  }
+}
+
+void compute_jacobi_scaling(psfm_ba_solver* S) {
+  k_scale_cams<<<(S->NS + 127) / 128, 128, 0, S->stream>>>(S->d_lin.p, S->d_lin.p + (size_t)S->F * NVL, S->d_active.p,
+                                                         S->F, S->C, S->d_scale_c.p);
+  PSFM_LAUNCH_CHECK();
+  if (S->P) {
+    k_scale_points<<<(S->P + 255) / 256, 256, 0, S->stream>>>(S->d_hpp.p, S->P, S->d_scale_p.p);
+    PSFM_LAUNCH_CHECK();
+  }
+}
+
+// |x|^2 over the reduced program's parameter blocks at the current state
+double current_x_sqnorm(psfm_ba_solver* S) {
+  S->d_x2.zero(S->stream);
+  S->d_rep.zero(S->stream);
+  if (S->P) {
+    const size_t n = 3 * (size_t)S->P;
+    const unsigned g = (unsigned)std::min<size_t>((n + 255) / 256, 1184);
+    k_sqnorm<<<g, 256, 0, S->stream>>>(S->d_X[S->cur].p, n, S->d_x2.p);
+    PSFM_LAUNCH_CHECK();
+  }
+  dist::allreduce_sum(S->d_x2.p, 1, S->stream);
+  ApplyArgs a;
+  a.yc = S->d_zero.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
+  a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
+  a.pose_c = S->d_pose[1 - S->cur].p; a.K_c = S->d_K[1 - S->cur].p;
+  a.F = S->F; a.C = S->C; a.acc = S->d_rep.p;
+  const int n = S->F + S->C;
+  k_apply_cams<<<(n + 255) / 256, 256, 0, S->stream>>>(a);
+  PSFM_LAUNCH_CHECK();
+  d2h(S, &S->hs->x2, S->d_x2.p, 1);
+  d2h(S, S->hs->rep, S->d_rep.p, 2);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  return S->hs->x2 + S->hs->rep[1];
+}
+
+struct LinOut { double cost, gmax; };
+
+// EvaluateGradientAndJacobian + the quantities the loop head needs
+LinOut linearize_and_measure(psfm_ba_solver* S, const RunCfg& c, double radius, bool timed) {
+  do_linearize(S, c, timed);
+  S->d_gmax.zero(S->stream);
+  S->d_prep.zero(S->stream);
+  do_point_blocks(S, c, radius);
+  dist::allreduce_max(S->d_gmax.p, 1, S->stream);
+  do_cam_gmax(S);
+  d2h(S, &S->hs->lin_cost, S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI, 1);
+  d2h(S, &S->hs->gmax, S->d_gmax.p, 1);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  LinOut o;
+  o.cost = S->hs->lin_cost;
+  o.gmax = S->hs->gmax;
+  return o;
+}
+
+struct StepOut {
+  bool linear_ok;
+  int pcg_flag, pcg_iters;
+  double mcc, step_sq, cand_x2, cand_cost;
+};
+
+// LevenbergMarquardtStrategy::ComputeStep + ComputeCandidatePointAndEvaluateCost
+StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* nprod) {
+  StepOut so;
+  memset(&so, 0, sizeof(so));
+  do_reduced_setup(S, c, radius);
+  int max_it, iters = 0;
+  double q_tol, r_tol;
+  if (c.solver == PSFM_BA_SOLVER_ITERATIVE_SCHUR) {
+    q_tol = c.o.eta; r_tol = -1.0; max_it = c.o.max_linear_solver_iterations;
+  } else {
+    q_tol = 0.0; r_tol = c.o.exact_r_tolerance;
+    max_it = c.o.exact_max_iterations > 0 ? c.o.exact_max_iterations
+                                          : std::min(20000, std::max(1000, 5 * S->NS));
+  }
+  so.pcg_flag = do_pcg(S, c, q_tol, r_tol, max_it, &iters, nprod);
+  so.pcg_iters = iters;
+  // candidate: points (inside the back-substitution), poses/intrinsics, cost
+  S->d_step.zero(S->stream);
+  S->d_rep.zero(S->stream);
+  BackArgs b;
+  b.J = jac_of(S); b.hinv = S->d_hinv.p; b.w = S->d_w.p; b.yc = S->d_x.p; b.scale_p = S->d_scale_p.p;
+  b.X = S->d_X[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
+  PSFM_TILE_LAUNCH(k_back_substitute, 6, S, c.rot, b);
+  ApplyArgs a;
+  a.yc = S->d_x.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
+  a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
+  a.pose_c = S->d_pose[1 - S->cur].p; a.K_c = S->d_K[1 - S->cur].p;
+  a.F = S->F; a.C = S->C; a.acc = S->d_rep.p;
+  const int n = S->F + S->C;
+  k_apply_cams<<<(n + 255) / 256, 256, 0, S->stream>>>(a);
+  PSFM_LAUNCH_CHECK();
+  if (S->M) {
+    CostArgs ca;
+    ca.pose = S->d_pose[1 - S->cur].p; ca.X = S->d_X[1 - S->cur].p; ca.K = S->d_K[1 - S->cur].p;
+    ca.loss.type = c.o.loss_function_type; ca.loss.a = c.o.loss_function_scale;
+    ca.acc_cost = S->d_step.p + 3;
+    const unsigned g = (unsigned)std::min<size_t>(((size_t)S->M + 255) / 256, 148 * 8);
+    k_cost<<<g, 256, 0, S->stream>>>(S->tc(), ca);
+    PSFM_LAUNCH_CHECK();
+  }
+  dist::allreduce_sum(S->d_step.p, 4, S->stream);
+  d2h(S, S->hs->step, S->d_step.p, 4);
+  d2h(S, S->hs->rep, S->d_rep.p, 2);
+  d2h(S, &S->hs->prep_fail, S->d_prep.p + (size_t)S->F * NVL + (size_t)S->C * NVI, 1);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  so.linear_ok = (so.pcg_flag != PCG_FAILURE) && !(S->hs->prep_fail > 0.0);
+  so.mcc = -S->hs->step[0];
+  so.step_sq = S->hs->step[1] + S->hs->rep[0];
+  so.cand_x2 = S->hs->step[2] + S->hs->rep[1];
+  so.cand_cost = S->hs->step[3];
+  if (!std::isfinite(so.mcc) || !std::isfinite(so.step_sq) || !std::isfinite(so.cand_cost)) {
+    // IsArrayValid(step) failed somewhere -> LINEAR_SOLVER_FAILURE
+    if (!std::isfinite(so.mcc) || !std::isfinite(so.step_sq)) so.linear_ok = false;
+  }
+  return so;
+}
+
+int count_observed_points_all_ranks(psfm_ba_solver* S) {
+  // every point lives on exactly one rank
+  if (dist::world_size() == 1) return S->P;
+  S->d_x2.zero(S->stream);
+  k_fill<<<1, 32, 0, S->stream>>>(S->d_x2.p, (double)S->P, 1);
+  PSFM_LAUNCH_CHECK();
+  dist::allreduce_sum(S->d_x2.p, 1, S->stream);
+  d2h(S, &S->hs->x2, S->d_x2.p, 1);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  return (int)(S->hs->x2 + 0.5);
+}
+
+int total_observations_all_ranks(psfm_ba_solver* S) {
+  if (dist::world_size() == 1) return S->M;
+  k_fill<<<1, 32, 0, S->stream>>>(S->d_x2.p, (double)S->M, 1);
+  PSFM_LAUNCH_CHECK();
+  dist::allreduce_sum(S->d_x2.p, 1, S->stream);
+  d2h(S, &S->hs->x2, S->d_x2.p, 1);
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  return (int)(S->hs->x2 + 0.5);
+}
+
+void print_summary(const psfm_ba_summary& s) {
+  // PrintSolverSummary, bundle_adjustment.cc:560-614
+  static const char* tn[] = {"Convergence", "Convergence", "Convergence", "No convergence", "Failure", "Convergence"};
+  printf("    Residuals : %d\n   Parameters : %d\n   Iterations : %d\n         Time : %g [s]\n"
+         " Initial cost : %.6g [px]\n   Final cost : %.6g [px]\n  Termination : %s\n\n",
+         s.num_residuals_reduced, s.num_effective_parameters_reduced, s.num_successful_steps + s.num_unsuccessful_steps,
+         s.total_time_in_seconds, std::sqrt(s.initial_cost / s.num_residuals_reduced),
+         std::sqrt(s.final_cost / s.num_residuals_reduced), tn[s.termination]);
+}
+
+int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* out) {
+  RunCfg c;
+  int rc = resolve_cfg(S, opts, c);
+  if (rc != PSFM_OK) return rc;
+  const psfm_ba_options& o = c.o;
+  psfm_ba_summary s;
+  memset(&s, 0, sizeof(s));
+  s.world_size = dist::world_size();
+  s.linear_solver_used = c.solver;
+  const int M_all = total_observations_all_ranks(S);
+  if (M_all == 0) {
+    if (o.print_summary) printf("Zero residual for BA\n");
+    if (out) *out = s;
+    return PSFM_ZERO_RESIDUALS;
+  }
+  const double t0 = now_s();
+  ensure_jac(S, c);
+  S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
+  upload_state(S);
+  set_masks_and_unit_scale(S, c);
+  s.num_residuals_reduced = 2 * M_all;
+  s.num_effective_parameters_reduced = c.num_effective_parameters + 3 * count_observed_points_all_ranks(S);
+
+  cudaEvent_t ev_begin = S->events.get(), ev_end = S->events.get();
+  PSFM_CUDA(cudaEventRecord(ev_begin, S->stream));
+
+  // ---- TrustRegionMinimizer::Minimize ----
+  double radius = o.initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  int num_invalid = 0, iteration = 0, nprod = 0;
+  // iteration 0: evaluate; jacobi scaling from the unscaled Jacobian, then re-linearise scaled
+  LinOut lo;
+  if (o.jacobi_scaling) {
+    do_linearize(S, c, false);
+    compute_jacobi_scaling(S);
+  }
+  lo = linearize_and_measure(S, c, radius, true);
+  s.num_linearize = 1;
+  double x_cost = lo.cost, gmax = lo.gmax;
+  double x_norm = std::sqrt(current_x_sqnorm(S));
+  s.initial_cost = x_cost;
+  int term = PSFM_TERM_NO_CONVERGENCE;
+  bool step_ok_prev = true, points_ready = true;
+  if (o.minimizer_progress_to_stdout)
+    printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter\n%4d % .6e  % .3e  % .3e\n",
+           0, x_cost, 0.0, gmax);
+  for (;;) {
+    if (step_ok_prev && iteration > 0) s.num_successful_steps++;
+    if (iteration >= o.max_num_iterations) { term = PSFM_TERM_NO_CONVERGENCE; break; }
+    if (gmax <= o.gradient_tolerance) { term = PSFM_TERM_CONVERGENCE_GRADIENT; break; }
+    if (radius <= o.min_trust_region_radius) { term = PSFM_TERM_MIN_RADIUS; break; }
+    ++iteration;
+    step_ok_prev = false;
+    (void)points_ready;
+    const StepOut so = compute_step(S, c, radius, &nprod);
+    s.num_linear_iterations += so.pcg_iters;
+    const bool valid = so.linear_ok && so.mcc > 0.0;
+    if (!valid) {
+      // HandleInvalidStep -> LevenbergMarquardtStrategy::StepIsInvalid == StepRejected(0)
+      s.num_unsuccessful_steps++;
+      if (++num_invalid >= o.max_num_consecutive_invalid_steps) { term = PSFM_TERM_FAILURE; break; }
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      continue;
+    }
+    num_invalid = 0;
+    const double step_norm = std::sqrt(so.step_sq);
+    if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) { term = PSFM_TERM_CONVERGENCE_PARAMETER; break; }
+    const double cost_change = x_cost - so.cand_cost;
+    if (std::fabs(cost_change) <= o.function_tolerance * x_cost) { term = PSFM_TERM_CONVERGENCE_FUNCTION; break; }
+    const double rho = cost_change / so.mcc;
+    if (rho > o.min_relative_decrease) {
+      S->cur = 1 - S->cur;   // x = candidate
+      x_norm = std::sqrt(so.cand_x2);
+      const double t = 2.0 * rho - 1.0;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
+      radius = std::min(o.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      lo = linearize_and_measure(S, c, radius, true);
+      s.num_linearize++;
+      x_cost = lo.cost;
+      gmax = lo.gmax;
+      step_ok_prev = true;
+    } else {
+      s.num_unsuccessful_steps++;
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+    }
+    if (o.minimizer_progress_to_stdout)
+      printf("%4d % .6e  % .3e  % .3e  % .3e  % .3e  % .3e  %d\n", iteration, step_ok_prev ? x_cost : so.cand_cost,
+             cost_change, gmax, step_norm, rho, radius, so.pcg_iters);
+  }
+  PSFM_CUDA(cudaEventRecord(ev_end, S->stream));
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  float ms = 0.f;
+  PSFM_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+  s.device_ms = ms;
+  for (auto& e : S->ev_lin) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.linearize_ms += ms; }
+  for (auto& e : S->ev_sp) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_product_ms += ms; }
+  s.num_linearize = (int)S->ev_lin.size();
+  s.num_schur_products = (int)S->ev_sp.size();
+  s.num_iterations = iteration;
+  s.termination = term;
+  s.final_cost = x_cost;
+  download_state(S);
+  s.total_time_in_seconds = now_s() - t0;
+  if (o.print_summary && dist::rank() == 0) print_summary(s);
+  if (out) *out = s;
+  return PSFM_OK;
+}
+
+int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (this library has no CPU path)");
+    return PSFM_ERR_NO_DEVICE;
+  }
+  return PSFM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI
+
+extern "C" void psfm_ba_default_options(psfm_ba_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->loss_function_type = PSFM_LOSS_TRIVIAL;   // bundle_adjustment.h:51
+  o->loss_function_scale = 1.0;                // :54
+  o->refine_focal_length = 1;                  // :57
+  o->refine_principal_point = 0;               // :60
+  o->refine_extra_params = 1;                  // :63
+  o->refine_extrinsics = 1;                    // :66
+  o->refine_rotation = 1;                      // :69
+  o->print_summary = 1;                        // :72
+  o->minimizer_progress_to_stdout = 0;         // :86
+  o->function_tolerance = 0.0;                 // :83
+  o->gradient_tolerance = 0.0;                 // :84
+  o->parameter_tolerance = 0.0;                // :85
+  o->max_num_iterations = 100;                 // :87
+  o->max_linear_solver_iterations = 200;       // :88
+  o->max_num_consecutive_invalid_steps = 10;   // :89
+  o->linear_solver = PSFM_BA_SOLVER_AUTO;
+  o->eta = 1e-1;                               // Ceres default
+  o->exact_r_tolerance = 1e-10;
+  o->exact_max_iterations = 0;
+  o->initial_trust_region_radius = 1e4;        // Ceres defaults
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->jacobi_scaling = 1;
+  o->pcg_check_period = 0;
+}
+
+extern "C" void psfm_ba_global_options(psfm_ba_options* o) {
+  // GlobalMapperOptions::GlobalBundleAdjustment, controllers/global_mapper.cc:41-71
+  psfm_ba_default_options(o);
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1.0;
+  o->parameter_tolerance = 1e-8;
+  o->max_num_iterations = 50;
+  o->max_linear_solver_iterations = 100;
+  o->minimizer_progress_to_stdout = 1;
+  o->print_summary = 1;
+  o->refine_rotation = 0;
+  o->refine_focal_length = 0;
+  o->refine_principal_point = 0;
+  o->refine_extra_params = 0;
+  o->loss_function_type = PSFM_LOSS_SOFT_L1;
+}
+
+extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
+  if (!pb || !out) { set_error("psfm_ba_create: null argument"); return PSFM_ERR_INVALID; }
+  *out = nullptr;
+  int rc = check_device();
+  if (rc != PSFM_OK) return rc;
+  psfm_ba_solver* S = new psfm_ba_solver();
+  try {
+    PSFM_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+    rc = build_structure(S, pb);
+    if (rc != PSFM_OK) { delete S; return rc; }
+    S->h_qvec.assign(pb->qvec, pb->qvec + 4 * (size_t)S->F);
+    S->h_tvec.assign(pb->tvec, pb->tvec + 3 * (size_t)S->F);
+    S->h_xyz.assign(pb->xyz, pb->xyz + 3 * (size_t)S->P_total);
+    S->h_K.assign(pb->cam_params, pb->cam_params + 3 * (size_t)S->C);
+    alloc_work(S);
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  } catch (const CudaFail& f) {
+    delete S;
+    return f.code;
+  }
+  *out = S;
+  return PSFM_OK;
+}
+
+extern "C" int psfm_ba_set_state(psfm_ba_solver* S, const double* qvec, const double* tvec, const double* xyz,
+                                 const double* cam_params) {
+  if (!S) return PSFM_ERR_INVALID;
+  if (qvec) S->h_qvec.assign(qvec, qvec + 4 * (size_t)S->F);
+  if (tvec) S->h_tvec.assign(tvec, tvec + 3 * (size_t)S->F);
+  if (xyz) S->h_xyz.assign(xyz, xyz + 3 * (size_t)S->P_total);
+  if (cam_params) S->h_K.assign(cam_params, cam_params + 3 * (size_t)S->C);
+  return PSFM_OK;
+}
+
+extern "C" int psfm_ba_get_state(psfm_ba_solver* S, double* qvec, double* tvec, double* xyz, double* cam_params) {
+  if (!S) return PSFM_ERR_INVALID;
+  if (qvec) memcpy(qvec, S->h_qvec.data(), sizeof(double) * S->h_qvec.size());
+  if (tvec) memcpy(tvec, S->h_tvec.data(), sizeof(double) * S->h_tvec.size());
+  if (xyz) memcpy(xyz, S->h_xyz.data(), sizeof(double) * S->h_xyz.size());
+  if (cam_params) memcpy(cam_params, S->h_K.data(), sizeof(double) * S->h_K.size());
+  return PSFM_OK;
+}
+
+extern "C" int psfm_ba_run(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* summary) {
+  if (!S) return PSFM_ERR_INVALID;
+  try {
+    return run_impl(S, opts, summary);
+  } catch (const CudaFail& f) {
+    return f.code;
+  }
+}
+
+extern "C" void psfm_ba_destroy(psfm_ba_solver* S) { delete S; }
+
+extern "C" int psfm_ba_solve(psfm_ba_problem* pb, const psfm_ba_options* opts, psfm_ba_summary* summary) {
+  if (!pb) return PSFM_ERR_INVALID;
+  if (pb->num_observations == 0 && dist::world_size() == 1) {
+    psfm_ba_options o;
+    if (opts) o = *opts; else psfm_ba_default_options(&o);
+    if (o.print_summary) printf("Zero residual for BA\n");
+    if (summary) memset(summary, 0, sizeof(*summary));
+    return PSFM_ZERO_RESIDUALS;
+  }
+  psfm_ba_solver* S = nullptr;
+  int rc = psfm_ba_create(pb, &S);
+  if (rc != PSFM_OK) return rc;
+  rc = psfm_ba_run(S, opts, summary);
+  if (rc == PSFM_OK) psfm_ba_get_state(S, pb->qvec, pb->tvec, pb->xyz, pb->cam_params);
+  psfm_ba_destroy(S);
+  return rc;
+}
+
+extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, double* cost, double* residuals,
+                                double* gradient_cam, double* gradient_pts) {
+  if (!S) return PSFM_ERR_INVALID;
+  try {
+    RunCfg c;
+    int rc = resolve_cfg(S, opts, c);
+    if (rc != PSFM_OK) return rc;
+    ensure_jac(S, c);
+    upload_state(S);
+    set_masks_and_unit_scale(S, c);
+    do_linearize(S, c, false);
+    const size_t F = S->F, C = S->C, M = S->M, P = S->P;
+    std::vector<double> lin(S->d_lin.n), r(2 * M), gp(3 * P);
+    d2h(S, lin.data(), S->d_lin.p, lin.size());
+    if (M) d2h(S, r.data(), S->d_r.p, 2 * M);
+    if (P) d2h(S, gp.data(), S->d_gp.p, 3 * P);
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    if (cost) *cost = lin[F * NVL + C * NVI];
+    if (residuals)
+      for (size_t j = 0; j < M; ++j) {
+        residuals[2 * (size_t)S->obs_orig[j]] = r[j];
+        residuals[2 * (size_t)S->obs_orig[j] + 1] = r[M + j];
+      }
+    if (gradient_cam) {
+      for (size_t i = 0; i < F; ++i)
+        for (int k = 0; k < 6; ++k) gradient_cam[6 * i + k] = lin[i * NVL + 12 + k];
+      for (size_t cc = 0; cc < C; ++cc)
+        for (int k = 0; k < 3; ++k) gradient_cam[6 * F + 3 * cc + k] = lin[F * NVL + cc * NVI + 6 + k];
+    }
+    if (gradient_pts) {
+      memset(gradient_pts, 0, sizeof(double) * 3 * (size_t)S->P_total);
+      for (size_t id = 0; id < P; ++id)
+        for (int k = 0; k < 3; ++k) gradient_pts[3 * (size_t)S->pt_orig[id] + k] = gp[k * P + id];
+    }
+    return PSFM_OK;
+  } catch (const CudaFail& f) {
+    return f.code;
+  }
+}
+
+extern "C" int psfm_ba_linear_step(psfm_ba_solver* S, const psfm_ba_options* opts, double radius, double* step_cam,
+                                   double* step_pts, int32_t* num_linear_iterations) {
+  if (!S) return PSFM_ERR_INVALID;
+  try {
+    RunCfg c;
+    int rc = resolve_cfg(S, opts, c);
+    if (rc != PSFM_OK) return rc;
+    ensure_jac(S, c);
+    S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
+    upload_state(S);
+    set_masks_and_unit_scale(S, c);
+    if (c.o.jacobi_scaling) { do_linearize(S, c, false); compute_jacobi_scaling(S); }
+    linearize_and_measure(S, c, radius, false);
+    int nprod = 0;
+    const StepOut so = compute_step(S, c, radius, &nprod);
+    const size_t NS = S->NS, P = S->P;
+    std::vector<double> yc(NS), X(3 * P), Xc(3 * P), sp(3 * P);
+    d2h(S, yc.data(), S->d_x.p, NS);
+    if (P) {
+      d2h(S, X.data(), S->d_X[S->cur].p, 3 * P);
+      d2h(S, Xc.data(), S->d_X[1 - S->cur].p, 3 * P);
+      d2h(S, sp.data(), S->d_scale_p.p, 3 * P);
+    }
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    if (step_cam) for (size_t k = 0; k < NS; ++k) step_cam[k] = -yc[k];
+    if (step_pts) {
+      memset(step_pts, 0, sizeof(double) * 3 * (size_t)S->P_total);
+      for (size_t id = 0; id < P; ++id)
+        for (int k = 0; k < 3; ++k)
+          step_pts[3 * (size_t)S->pt_orig[id] + k] = (Xc[3 * id + k] - X[3 * id + k]) / sp[3 * id + k];
+    }
+    if (num_linear_iterations) *num_linear_iterations = so.pcg_iters;
+    return so.linear_ok ? PSFM_OK : PSFM_ERR_INVALID;
+  } catch (const CudaFail& f) {
+    return f.code;
+  }
+}

@@ -1,0 +1,157 @@
+"""HP2 parity on the GPU, through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from particlesfm_b200 import _abi, ba, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _opts(rot, focal, solver, pp=False):
+    o = oracle.ba_global_options(refine_rotation=rot, refine_focal_length=focal)
+    o.refine_principal_point = int(pp)
+    o.linear_solver = solver
+    return o
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+PASSES = [(False, False), (True, True), (True, False)]
+
+
+@pytest.mark.parametrize("rot,focal", PASSES)
+def test_evaluate_matches_oracle(gpu, rot, focal):
+    prob, _ = syn.make_ba_problem(12, 900, 6, seed=3, track_len_range=(2, 9))
+    o = _opts(rot, focal, _abi.SOLVER_EXACT_SCHUR)
+    c0, r0, gc0, gp0 = oracle.ba_evaluate(prob, o)
+    S = ba.ResidentSolver(prob)
+    c1, r1, gc1, gp1 = S.evaluate(o)
+    assert abs(c1 - c0) <= 1e-12 * abs(c0)
+    assert _rel(r1, r0) < 1e-12
+    assert _rel(gc1, gc0) < 1e-10
+    assert _rel(gp1, gp0) < 1e-10
+
+
+def test_evaluate_principal_point_and_losses(gpu):
+    prob, _ = syn.make_ba_problem(8, 400, 5, seed=4)
+    for loss in (_abi.LOSS_TRIVIAL, _abi.LOSS_SOFT_L1, _abi.LOSS_CAUCHY):
+        o = _opts(True, True, _abi.SOLVER_EXACT_SCHUR, pp=True)
+        o.loss_function_type = loss
+        c0, r0, gc0, gp0 = oracle.ba_evaluate(prob, o)
+        c1, r1, gc1, gp1 = ba.ResidentSolver(prob).evaluate(o)
+        assert abs(c1 - c0) <= 1e-12 * abs(c0)
+        assert _rel(r1, r0) < 1e-12 and _rel(gc1, gc0) < 1e-10 and _rel(gp1, gp0) < 1e-10
+
+
+@pytest.mark.parametrize("rot,focal", PASSES)
+def test_linear_step_matches_cholesky(gpu, rot, focal):
+    prob, _ = syn.make_ba_problem(10, 600, 6, seed=5)
+    o = _opts(rot, focal, _abi.SOLVER_EXACT_SCHUR)
+    for radius in (1e4, 1e1):
+        sc0, sp0, _ = oracle.ba_linear_step(prob, o, radius, _abi.SOLVER_EXACT_SCHUR)
+        sc1, sp1, it = ba.ResidentSolver(prob).linear_step(o, radius)
+        assert it > 0
+        assert _rel(sc1, sc0) < 1e-6, (rot, focal, radius, _rel(sc1, sc0))
+        assert _rel(sp1, sp0) < 1e-6
+
+
+def test_iterative_linear_step_matches_oracle_pcg(gpu):
+    # same algorithm (ConjugateGradientsSolver + SCHUR_JACOBI, eta = 0.1) on both sides
+    prob, _ = syn.make_ba_problem(10, 600, 6, seed=6)
+    o = _opts(True, True, _abi.SOLVER_ITERATIVE_SCHUR)
+    sc0, sp0, it0 = oracle.ba_linear_step(prob, o, 1e4, _abi.SOLVER_ITERATIVE_SCHUR)
+    sc1, sp1, it1 = ba.ResidentSolver(prob).linear_step(o, 1e4)
+    assert it1 == it0
+    assert _rel(sc1, sc0) < 1e-7 and _rel(sp1, sp0) < 1e-7
+
+
+@pytest.mark.parametrize("rot,focal", PASSES)
+def test_full_solve_exact_mode(gpu, rot, focal):
+    """Final poses / points within 1e-5 relative of the oracle (north-star tolerance),
+    same iteration counts, gauge parameters bit-identical to the input."""
+    prob, truth = syn.make_ba_problem(16, 1500, 7, seed=7)
+    o = _opts(rot, focal, _abi.SOLVER_EXACT_SCHUR)
+    p0, p1 = prob.copy(), prob.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert s1.termination == s0.termination
+    assert s1.num_iterations == s0.num_iterations
+    assert s1.num_successful_steps == s0.num_successful_steps
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-5 * s0.final_cost
+    assert abs(s1.initial_cost - s0.initial_cost) <= 1e-10 * s0.initial_cost
+    for a, b in ((p1.qvec, p0.qvec), (p1.tvec, p0.tvec), (p1.xyz, p0.xyz), (p1.cam_params, p0.cam_params)):
+        assert _rel(a, b) < 1e-5
+    # gauge: constant pose of image 0 and tvec[0] of image 1
+    q0 = prob.qvec[0] / np.linalg.norm(prob.qvec[0])
+    assert np.array_equal(p1.qvec[0], q0) and np.array_equal(p1.tvec[0], prob.tvec[0])
+    assert p1.tvec[1, 0] == prob.tvec[1, 0]
+    if not rot:
+        qn = prob.qvec / np.linalg.norm(prob.qvec, axis=1, keepdims=True)
+        assert np.array_equal(p1.qvec, qn)
+    if not focal:
+        assert np.array_equal(p1.cam_params, prob.cam_params)
+
+
+def test_full_solve_iterative_mode(gpu):
+    prob, truth = syn.make_ba_problem(24, 3000, 8, seed=8)
+    o = _opts(True, True, _abi.SOLVER_ITERATIVE_SCHUR)
+    p0, p1 = prob.copy(), prob.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert s1.final_cost < 0.2 * s1.initial_cost
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-3 * s0.final_cost
+    ate = syn.umeyama_ate(syn.camera_centres(p1.qvec, p1.tvec), truth["centres"])
+    ate0 = syn.umeyama_ate(syn.camera_centres(p0.qvec, p0.tvec), truth["centres"])
+    assert abs(ate - ate0) < 1e-3      # "Sintel ATE within 1e-3 m of reference" stand-in
+
+
+def test_zero_noise_recovers_truth(gpu):
+    prob, truth = syn.make_ba_problem(12, 800, 6, seed=9, noise_px=0.0)
+    o = _opts(True, False, _abi.SOLVER_EXACT_SCHUR)
+    o.function_tolerance = 1e-14; o.gradient_tolerance = 1e-12; o.parameter_tolerance = 1e-14
+    o.max_num_iterations = 60
+    s = ba.solve_problem(prob, o)
+    assert s.final_cost < 1e-6 * s.initial_cost
+    assert syn.umeyama_ate(syn.camera_centres(prob.qvec, prob.tvec), truth["centres"]) < 1e-4
+
+
+def test_long_tracks_and_unobserved_points(gpu):
+    # tracks longer than 256 observations select the 512/1024-wide tiles; points without
+    # observations and images without observations are left untouched
+    prob, _ = syn.make_ba_problem(300, 40, 300, seed=10)
+    prob2, _ = syn.make_ba_problem(300, 400, 9, seed=11)
+    obs_image = np.concatenate([prob.obs_image, prob2.obs_image])
+    obs_point = np.concatenate([prob.obs_point, prob2.obs_point + 40])
+    keep = obs_image != 17                       # image 17 has no observation
+    xyz = np.concatenate([prob.xyz, prob2.xyz, np.full((5, 3), 123.0)])
+    p = _abi.BAProblem(prob.qvec, prob.tvec, xyz, prob.cam_params, obs_image[keep], obs_point[keep],
+                       np.concatenate([prob.obs_xy, prob2.obs_xy])[keep], prob.image_camera,
+                       prob.pose_constant, prob.tvec_constant_mask, prob.camera_constant)
+    o = _opts(True, True, _abi.SOLVER_ITERATIVE_SCHUR)
+    o.max_num_iterations = 6
+    p0, p1 = p.copy(), p.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert np.array_equal(p1.xyz[-5:], xyz[-5:])
+    assert np.array_equal(p1.tvec[17], p.tvec[17])
+    assert abs(s1.initial_cost - s0.initial_cost) <= 1e-10 * s0.initial_cost
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-2 * s0.final_cost
+
+
+def test_zero_residuals_and_errors(gpu):
+    prob, _ = syn.make_ba_problem(4, 10, 3, seed=12)
+    empty = _abi.BAProblem(prob.qvec, prob.tvec, prob.xyz, prob.cam_params, np.zeros(0, np.int32),
+                           np.zeros(0, np.int32), np.zeros((0, 2)), prob.image_camera)
+    import ctypes as C
+    from particlesfm_b200 import _lib
+    o = _opts(True, True, _abi.SOLVER_AUTO)
+    s = _abi.BASummary()
+    st = empty.struct()
+    assert _lib.lib().psfm_ba_solve(C.byref(st), C.byref(o), C.byref(s)) == _abi.PSFM_ZERO_RESIDUALS
+    bad = prob.copy()
+    bad.obs_image = bad.obs_image.copy(); bad.obs_image[0] = 99
+    st = bad.struct()
+    assert _lib.lib().psfm_ba_solve(C.byref(st), C.byref(o), C.byref(s)) == _abi.PSFM_ERR_INVALID
