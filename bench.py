@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--solver", default="iterative", choices=["iterative", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-traj", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +252,7 @@ def main():
 
     # ---------------- end to end through the C ABI on host buffers ----------------
     e2e_times = []
-    for k in range(1 + args.steps):
+    for k in range(0 if args.no_e2e else 1 + args.steps):
         p = prob.copy()
         p.qvec[:], p.tvec[:], p.xyz[:], p.cam_params[:] = init
         barrier()
@@ -260,7 +261,7 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         if k >= 1:
             e2e_times.append(dt)
-    e2e_val = M_total * len(e2e_times) / sum(e2e_times)
+    e2e_val = M_total * len(e2e_times) / sum(e2e_times) if e2e_times else None
     state_bytes = 8 * (full.qvec.size + full.tvec.size + full.cam_params.size) + 8 * 3 * np.unique(prob.obs_point).size
     h2d = prob.obs_xy.nbytes + prob.obs_image.nbytes + prob.obs_point.nbytes + 2 * prob.num_observations + 4 * prob.num_observations + state_bytes
     d2h = state_bytes
@@ -282,7 +283,7 @@ def main():
         "final_cost": s_last.final_cost, "initial_cost": s_last.initial_cost, "termination": s_last.termination,
         "ate_vs_truth": ate,
         "e2e": {"value": e2e_val, "unit": "observations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times)},
+                "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline, "roofline_linearize": roofline_lin,

@@ -84,6 +84,8 @@ typedef struct {
   double* gs_p;   /* 3P */
   double* step_c; double* step_p;
   double* S;      /* NS*NS (exact) */
+  double* Spriv;  /* private copies of S for the assembly threads */
+  int nspriv;
   double* tbuf;   /* per-thread scratch */
   size_t tbuf_stride;
   int num_linear_iterations;
@@ -596,16 +598,27 @@ static void build_schur_dense(ctx_t* c, double* S) {
   const int NS = c->NS, P = c->P, F = c->F;
   const psfm_ba_problem* pb = c->pb;
   const size_t nn = (size_t)NS * NS;
-  const int nbuf = c->nthreads;
-  /* per-thread copies when they fit in ~6 GB, else atomics */
+  /* the assembly runs on at most 16 threads, each with a private copy of S (kept for the
+     whole solve); more copies cost more in zeroing/merging than they gain */
+  const int nbuf = c->nthreads < 16 ? c->nthreads : 16;
   int use_private = (nn * sizeof(double) * (size_t)nbuf) < ((size_t)6 << 30);
   double* priv = NULL;
   if (use_private && nbuf > 1) {
-    priv = (double*)calloc(nn * (size_t)(nbuf - 1), sizeof(double));
+    if (!c->Spriv || c->nspriv != nbuf - 1) {
+      free(c->Spriv);
+      c->Spriv = (double*)malloc(nn * (size_t)(nbuf - 1) * sizeof(double));
+      c->nspriv = nbuf - 1;
+    }
+    priv = c->Spriv;
     if (!priv) use_private = 0;
   }
-  memset(S, 0, nn * sizeof(double));
-#pragma omp parallel num_threads(c->nthreads)
+#pragma omp parallel for schedule(static) num_threads(c->nthreads)
+  for (long long k = 0; k < (long long)nn; ++k) S[k] = 0.0;
+  if (priv) {
+#pragma omp parallel for schedule(static) num_threads(c->nthreads)
+    for (long long k = 0; k < (long long)(nn * (size_t)(nbuf - 1)); ++k) priv[k] = 0.0;
+  }
+#pragma omp parallel num_threads(nbuf)
   {
 #ifdef _OPENMP
     const int th = omp_get_thread_num();
@@ -613,7 +626,7 @@ static void build_schur_dense(ctx_t* c, double* S) {
     const int th = 0;
 #endif
     double* Sx = (use_private && th > 0) ? priv + nn * (size_t)(th - 1) : S;
-    const int atomic = !use_private && c->nthreads > 1;
+    const int atomic = !use_private && nbuf > 1;
     int wcap = 256;
     double* W = (double*)malloc(sizeof(double) * 27 * (size_t)wcap);  /* per obs: 6x3 pose | 3x3 intr */
     double* WH = (double*)malloc(sizeof(double) * 27 * (size_t)wcap); /* W * Hinv */
@@ -685,7 +698,6 @@ static void build_schur_dense(ctx_t* c, double* S) {
       for (int th = 0; th < nbuf - 1; ++th) s += priv[nn * (size_t)th + k];
       S[k] = s;
     }
-    free(priv);
   }
 #pragma omp parallel for schedule(static) num_threads(c->nthreads)
   for (int i = 0; i < NS; ++i)
@@ -1027,7 +1039,8 @@ static int ctx_init(ctx_t* c, const psfm_ba_problem* pb, const psfm_ba_options* 
   c->pb = pb; c->o = *o;
   c->F = pb->num_images; c->P = pb->num_points; c->M = pb->num_observations; c->C = pb->num_cameras;
   c->NS = 6 * c->F + 3 * c->C;
-  if (nthreads <= 0) nthreads = psfm_oracle_num_threads();
+  /* num_threads = min(cpu_count, 64): sfm/main_sfm.py:144 (--GlobalMapper.num_threads) */
+  if (nthreads <= 0) nthreads = psfm_oracle_num_threads() < 64 ? psfm_oracle_num_threads() : 64;
   if (nthreads > MAXT) nthreads = MAXT;
   c->nthreads = nthreads;
   const int F = c->F, P = c->P, M = c->M, C = c->C, NS = c->NS;
@@ -1107,7 +1120,7 @@ static void ctx_free(ctx_t* c) {
   free(c->Xc); free(c->Kc); free(c->r); free(c->Jc); free(c->Jp); free(c->Jk); free(c->scale_c);
   free(c->scale_p); free(c->g_c); free(c->g_p); free(c->diag_c); free(c->diag_p); free(c->D_c);
   free(c->D_p); free(c->Hinv); free(c->gs_c); free(c->gs_p); free(c->step_c); free(c->step_p);
-  free(c->S); free(c->tbuf);
+  free(c->S); free(c->Spriv); free(c->tbuf);
 }
 
 /* EvaluateGradientAndJacobian: cost, r, J, g = J'r (unscaled), optional scaling */

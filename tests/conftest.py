@@ -13,11 +13,8 @@ def pytest_configure(config):
 
 
 def _have_gpu():
-    try:
-        import particlesfm_b200
-        return particlesfm_b200.device_count() > 0
-    except Exception:
-        return False
+    import particlesfm_b200
+    return particlesfm_b200.device_count() > 0
 
 
 @pytest.fixture(scope="session")
