@@ -8,7 +8,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsfm_b200.so")
+# PSFM_LIB: alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("PSFM_LIB") or os.path.join(_HERE, "libpsfm_b200.so")
 _LIB = None
 
 EXPORTS = [

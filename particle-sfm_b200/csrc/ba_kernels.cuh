@@ -22,6 +22,11 @@ namespace ba {
 
 constexpr int NVL = 18;   // camera-side accumulator stride per image
 constexpr int NVI = 9;    // intrinsics accumulator stride per camera
+// Concurrently resident tiles are consecutive tiles and therefore touch the SAME few
+// images: their fp64 REDs would serialise on a handful of L2 addresses.  Every per-image
+// accumulator is therefore replicated NREP times (replica = tile index mod NREP) and the
+// replicas are folded by k_fold_replicas before use.
+constexpr int NREP = 32;
 constexpr double kHuge = 1.7976931348623157e308;
 
 struct TileCtx {
@@ -101,26 +106,42 @@ struct TileInfo {
   int base, n, pt0, np, ns;
 };
 
-template <int TILE, int NV>
-__device__ __forceinline__ TileInfo tile_prologue(const TileCtx& tc, TileSmem<TILE, NV>& sm, bool need_cam) {
+// Tile header: five scalar loads.  The caller then issues ALL of its global loads
+// (observation data, Jacobian rows, per-point blocks) before tile_fill_smem(), so that a
+// CTA pays one global-memory latency for the whole batch instead of one per stage.
+__device__ __forceinline__ TileInfo tile_header(const TileCtx& tc, int& cs0) {
   TileInfo ti;
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  ti.base = tc.tile_start[tile];
-  ti.n = tc.tile_start[tile + 1] - ti.base;
-  ti.pt0 = tc.tile_pt[tile];
-  ti.np = tc.tile_pt[tile + 1] - ti.pt0;
-  const int cs0 = tc.cseg_ptr[tile];
-  ti.ns = tc.cseg_ptr[tile + 1] - cs0;
-  for (int j = tid; j <= ti.np; j += TILE) sm.pstart[j] = tc.pt_ptr[ti.pt0 + j] - ti.base;
+  const int tile = blockIdx.x;
+  ti.base = __ldg(tc.tile_start + tile);
+  ti.n = __ldg(tc.tile_start + tile + 1) - ti.base;
+  ti.pt0 = __ldg(tc.tile_pt + tile);
+  ti.np = __ldg(tc.tile_pt + tile + 1) - ti.pt0;
+  cs0 = __ldg(tc.cseg_ptr + tile);
+  ti.ns = __ldg(tc.cseg_ptr + tile + 1) - cs0;
+  return ti;
+}
+
+template <int TILE, int NV>
+__device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE, NV>& sm, const TileInfo& ti,
+                                               int cs0, bool need_cam) {
+  const int tid = threadIdx.x;
+  for (int j = tid; j <= ti.np; j += TILE) sm.pstart[j] = __ldg(tc.pt_ptr + ti.pt0 + j) - ti.base;
   if (need_cam) {
     for (int j = tid; j < ti.ns; j += TILE) {
-      sm.coff[j] = tc.cseg_off[cs0 + j];
-      sm.cimg[j] = tc.cseg_img[cs0 + j];
+      sm.coff[j] = __ldg(tc.cseg_off + cs0 + j);
+      sm.cimg[j] = __ldg(tc.cseg_img + cs0 + j);
     }
     if (tid == 0) sm.coff[ti.ns] = ti.n;
-    if (tid < ti.n) sm.perm[tid] = tc.tile_perm[ti.base + tid];
+    if (tid < ti.n) sm.perm[tid] = __ldg(tc.tile_perm + ti.base + tid);
   }
   __syncthreads();
+}
+
+template <int TILE, int NV>
+__device__ __forceinline__ TileInfo tile_prologue(const TileCtx& tc, TileSmem<TILE, NV>& sm, bool need_cam) {
+  int cs0;
+  const TileInfo ti = tile_header(tc, cs0);
+  tile_fill_smem<TILE, NV>(tc, sm, ti, cs0, need_cam);
   return ti;
 }
 
@@ -195,7 +216,8 @@ struct LinArgs {
   double* hpp;            // [6][P]  E'E (upper: 00 01 02 11 12 22)
   double* gp;             // [3][P]  E'r
   double* wk;             // [9][P]  (G'E) rows: focal (3) | cx (3) | cy (3)
-  double* acc_cam;        // [F][NVL] rot F'F (6) | t F'F (6) | g (6)
+  double* acc_cam;        // [NREP][F][NVL] rot F'F (6) | t F'F (6) | g (6)
+  size_t rep_stride;      // doubles between replicas
   double* acc_intr;       // [C][NVI] G'G (6: ff fx fy xx xy yy) | g_k (3)
   double* acc_cost;       // [1]
 };
@@ -205,11 +227,20 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE, 18> sm;
   sm.carve(smem_raw);
-  const TileInfo ti = tile_prologue<TILE, 18>(tc, sm, true);
+  int cs0;
+  const TileInfo ti = tile_header(tc, cs0);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
   const int M = tc.M;
   const size_t i = (size_t)ti.base + tid;
+  int img = 0, pt = 0;
+  double2 xy = make_double2(0.0, 0.0);
+  if (act) {
+    img = __ldg(tc.obs_img + i);
+    pt = __ldg(tc.obs_pt + i);
+    xy = tc.obs_xy[i];
+  }
+  tile_fill_smem<TILE, 18>(tc, sm, ti, cs0, true);
 
   double r0 = 0, r1 = 0, cost = 0;
   double jr[2][3], jt[2][3], jp[2][3], jk[4];
@@ -218,12 +249,9 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const
 #pragma unroll
     for (int b_ = 0; b_ < 3; ++b_) { jr[a_][b_] = 0; jt[a_][b_] = 0; jp[a_][b_] = 0; }
   jk[0] = jk[1] = jk[2] = jk[3] = 0;
-  int img = 0, pt = 0, cam = 0;
+  int cam = 0;
   if (act) {
-    img = tc.obs_img[i];
-    pt = tc.obs_pt[i];
     cam = tc.img_cam[img];
-    const double2 xy = tc.obs_xy[i];
     double q[4], t[3];
     load_pose(a.pose, img, q, t);
     const double X[3] = {a.X[3 * (size_t)pt], a.X[3 * (size_t)pt + 1], a.X[3 * (size_t)pt + 2]};
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const
       const double* row = sm.sv + k * TILE;
       double acc = 0.0;
       for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-      atomicAdd(a.acc_cam + (size_t)sm.cimg[s] * NVL + k, acc);
+      atomicAdd(a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + (size_t)sm.cimg[s] * NVL + k, acc);
     }
   }
   // ---- cost and intrinsics (block sums) ----
@@ -487,7 +515,8 @@ struct PrepArgs {
   Jac J;
   const double* hinv;   // [6][P]
   const double* w;      // [3][P]
-  double* acc_cam;      // [F][NVL]: -(W hinv W') rot (6) | t (6) | -(W w) (6)
+  double* acc_cam;      // [NREP][F][NVL]: -(W hinv W') rot (6) | t (6) | -(W w) (6)
+  size_t rep_stride;
 };
 
 template <int TILE, bool ROT>
@@ -495,31 +524,37 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE, 18> sm;
   sm.carve(smem_raw);
-  const TileInfo ti = tile_prologue<TILE, 18>(tc, sm, true);
+  int cs0;
+  const TileInfo ti = tile_header(tc, cs0);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
   const size_t M = tc.M, P = tc.P;
   const size_t i = (size_t)ti.base + tid;
-  double* sv = sm.sv + tid;
+  constexpr int NCP = ROT ? 6 : 3;
+  double jp[2][3], hv[6], w[3], jcr0[NCP], jcr1[NCP];
   if (act) {
-    const int pt = tc.obs_pt[i];
-    double jp[2][3], hv[6], w[3];
+    const int pt = __ldg(tc.obs_pt + i);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
+#pragma unroll
+    for (int k = 0; k < NCP; ++k) { jcr0[k] = a.J.jc[(size_t)k * M + i]; jcr1[k] = a.J.jc[(size_t)(NCP + k) * M + i]; }
 #pragma unroll
     for (int k = 0; k < 6; ++k) hv[k] = a.hinv[k * P + pt];
 #pragma unroll
     for (int k = 0; k < 3; ++k) w[k] = a.w[k * P + pt];
+  }
+  tile_fill_smem<TILE, 18>(tc, sm, ti, cs0, true);
+  double* sv = sm.sv + tid;
+  if (act) {
     // block b: 0 = rot (ROT only), 1 = translation
 #pragma unroll
     for (int b = (ROT ? 0 : 1); b < 2; ++b) {
       double jc0[3], jc1[3];
       const int off = ROT ? 3 * b : 0;
-      const int stride = ROT ? 6 : 3;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        jc0[k] = a.J.jc[(size_t)(off + k) * M + i];
-        jc1[k] = a.J.jc[(size_t)(stride + off + k) * M + i];
+        jc0[k] = jcr0[off + k];
+        jc1[k] = jcr1[off + k];
       }
       double W[3][3], WH[3][3];
 #pragma unroll
@@ -550,7 +585,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
     const double* row = sm.sv + k * TILE;
     double acc = 0.0;
     for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-    atomicAdd(a.acc_cam + (size_t)sm.cimg[s] * NVL + k, acc);
+    atomicAdd(a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + (size_t)sm.cimg[s] * NVL + k, acc);
   }
 }
 
@@ -560,24 +595,30 @@ struct SpArgs {
   Jac J;
   const double* hinv;   // [6][P]
   const double* x;      // [6F + 3C] input vector (slot layout)
-  double* y;            // [6F + 3C] += F'(I - E hinv E') F x   (D^2 x is added by the PCG kernel)
+  double* y;            // [NREP][6F + 3C] += F'(I - E hinv E') F x  (D^2 x is added by the PCG kernel)
+  size_t rep_stride;
   const int* flag;      // PCG state: != 0 -> nothing to do
   int intr;
 };
 
+#ifndef PSFM_SP_MINB
+#define PSFM_SP_MINB 3
+#endif
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_schur_product(const TileCtx tc, const SpArgs a) {
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schur_product(const TileCtx tc, const SpArgs a) {
   if (*a.flag != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE, 6> sm;
   sm.carve(smem_raw);
-  const TileInfo ti = tile_prologue<TILE, 6>(tc, sm, true);
+  int cs0;
+  const TileInfo ti = tile_header(tc, cs0);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
   const size_t M = tc.M, P = tc.P;
   const size_t i = (size_t)ti.base + tid;
   constexpr int NC = ROT ? 6 : 3;
   double jc0[NC], jc1[NC], jp[2][3], jk[4] = {0, 0, 0, 0};
+  double hp[6] = {0, 0, 0, 0, 0, 0};
   double u0 = 0, u1 = 0;
   int img = 0, lp = 0;
   const double* xk = a.x + 6 * (size_t)tc.F;   // single shared camera when intr > 0
@@ -585,22 +626,32 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_schur_product(c
   for (int k = 0; k < NC; ++k) { jc0[k] = 0; jc1[k] = 0; }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { jp[0][k] = 0; jp[1][k] = 0; }
+  // ---- every global load of the tile is issued here, before the first barrier ----
   if (act) {
-    img = tc.obs_img[i];
-    lp = tc.obs_pt[i] - ti.pt0;
+    img = __ldg(tc.obs_img + i);
+    lp = __ldg(tc.obs_pt + i) - ti.pt0;
 #pragma unroll
     for (int k = 0; k < NC; ++k) { jc0[k] = a.J.jc[(size_t)k * M + i]; jc1[k] = a.J.jc[(size_t)(NC + k) * M + i]; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
+    if (a.intr >= 1) {
+      jk[0] = a.J.jk[i]; jk[1] = a.J.jk[M + i];
+      if (a.intr == 3) { jk[2] = a.J.jk[2 * M + i]; jk[3] = a.J.jk[3 * M + i]; }
+    }
+  }
+  if (tid < ti.np) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hp[k] = a.hinv[k * P + (size_t)ti.pt0 + tid];
+  }
+  tile_fill_smem<TILE, 6>(tc, sm, ti, cs0, true);
+  if (act) {
     const double* xi = a.x + 6 * (size_t)img + (ROT ? 0 : 3);
 #pragma unroll
     for (int k = 0; k < NC; ++k) { const double xv = __ldg(xi + k); u0 += jc0[k] * xv; u1 += jc1[k] * xv; }
     if (a.intr >= 1) {
-      jk[0] = a.J.jk[i]; jk[1] = a.J.jk[M + i];
       const double xf = __ldg(xk);
       u0 += jk[0] * xf; u1 += jk[1] * xf;
       if (a.intr == 3) {
-        jk[2] = a.J.jk[2 * M + i]; jk[3] = a.J.jk[3 * M + i];
         u0 += jk[2] * __ldg(xk + 1);
         u1 += jk[3] * __ldg(xk + 2);
       }
@@ -620,13 +671,10 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_schur_product(c
   }
   __syncthreads();
   if (tid < ti.np) {
-    const size_t gp_ = (size_t)ti.pt0 + tid;
     const double t0 = sm.sw[tid], t1 = sm.sw[TILE + tid], t2 = sm.sw[2 * TILE + tid];
-    const double h0 = a.hinv[gp_], h1 = a.hinv[P + gp_], h2 = a.hinv[2 * P + gp_], h3 = a.hinv[3 * P + gp_],
-                 h4 = a.hinv[4 * P + gp_], h5 = a.hinv[5 * P + gp_];
-    sm.sw[tid] = h0 * t0 + h1 * t1 + h2 * t2;
-    sm.sw[TILE + tid] = h1 * t0 + h3 * t1 + h4 * t2;
-    sm.sw[2 * TILE + tid] = h2 * t0 + h4 * t1 + h5 * t2;
+    sm.sw[tid] = hp[0] * t0 + hp[1] * t1 + hp[2] * t2;
+    sm.sw[TILE + tid] = hp[1] * t0 + hp[3] * t1 + hp[4] * t2;
+    sm.sw[2 * TILE + tid] = hp[2] * t0 + hp[4] * t1 + hp[5] * t2;
   }
   __syncthreads();
   const double w0 = sm.sw[lp], w1 = sm.sw[TILE + lp], w2 = sm.sw[2 * TILE + lp];
@@ -641,7 +689,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_schur_product(c
     const double* row = sm.sv + k * TILE;
     double acc = 0.0;
     for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-    atomicAdd(a.y + 6 * (size_t)sm.cimg[s] + (ROT ? 0 : 3) + k, acc);
+    atomicAdd(a.y + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + 6 * (size_t)sm.cimg[s] + (ROT ? 0 : 3) + k, acc);
   }
   if (a.intr >= 1) {
     double v[3];
@@ -649,7 +697,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_schur_product(c
     v[1] = act ? jk[2] * v0 : 0.0;
     v[2] = act ? jk[3] * v1 : 0.0;
     const double s = block_sum_multi<3>(v, sm.sred);
-    if (tid < a.intr) atomicAdd(a.y + 6 * (size_t)tc.F + tid, s);
+    if (tid < a.intr) atomicAdd(a.y + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + 6 * (size_t)tc.F + tid, s);
   }
 }
 
@@ -668,40 +716,61 @@ struct BackArgs {
 };
 
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE, 6> sm;
   sm.carve(smem_raw);
-  const TileInfo ti = tile_prologue<TILE, 6>(tc, sm, false);
+  int cs0;
+  const TileInfo ti = tile_header(tc, cs0);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
   const size_t M = tc.M, P = tc.P;
   const size_t i = (size_t)ti.base + tid;
   constexpr int NC = ROT ? 6 : 3;
-  double jp[2][3];
+  double jc0[NC], jc1[NC], jp[2][3], jk[4] = {0, 0, 0, 0};
   double u0 = 0, u1 = 0, r0 = 0, r1 = 0;
-  int lp = 0;
+  int img = 0, lp = 0;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { jc0[k] = 0; jc1[k] = 0; }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { jp[0][k] = 0; jp[1][k] = 0; }
+  // ---- all global loads up front ----
   if (act) {
-    const int img = tc.obs_img[i];
-    lp = tc.obs_pt[i] - ti.pt0;
+    img = __ldg(tc.obs_img + i);
+    lp = __ldg(tc.obs_pt + i) - ti.pt0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { jc0[k] = a.J.jc[(size_t)k * M + i]; jc1[k] = a.J.jc[(size_t)(NC + k) * M + i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
+    if (a.intr >= 1) {
+      jk[0] = a.J.jk[i]; jk[1] = a.J.jk[M + i];
+      if (a.intr == 3) { jk[2] = a.J.jk[2 * M + i]; jk[3] = a.J.jk[3 * M + i]; }
+    }
+    r0 = a.J.r[i]; r1 = a.J.r[M + i];
+  }
+  double hp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0}, spp[3] = {0, 0, 0}, Xp[3] = {0, 0, 0};
+  if (tid < ti.np) {
+    const size_t g = (size_t)ti.pt0 + tid;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hp[k] = a.hinv[k * P + g];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { wp[k] = a.w[k * P + g]; spp[k] = a.scale_p[3 * g + k]; Xp[k] = a.X[3 * g + k]; }
+  }
+  tile_fill_smem<TILE, 6>(tc, sm, ti, cs0, false);
+  if (act) {
     const double* xi = a.yc + 6 * (size_t)img + (ROT ? 0 : 3);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const double xv = __ldg(xi + k);
-      u0 += a.J.jc[(size_t)k * M + i] * xv;
-      u1 += a.J.jc[(size_t)(NC + k) * M + i] * xv;
+      u0 += jc0[k] * xv;
+      u1 += jc1[k] * xv;
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
     if (a.intr >= 1) {
       const double* xk = a.yc + 6 * (size_t)tc.F;
       const double xf = __ldg(xk);
-      u0 += a.J.jk[i] * xf; u1 += a.J.jk[M + i] * xf;
-      if (a.intr == 3) { u0 += a.J.jk[2 * M + i] * __ldg(xk + 1); u1 += a.J.jk[3 * M + i] * __ldg(xk + 2); }
+      u0 += jk[0] * xf; u1 += jk[1] * xf;
+      if (a.intr == 3) { u0 += jk[2] * __ldg(xk + 1); u1 += jk[3] * __ldg(xk + 2); }
     }
-    r0 = a.J.r[i]; r1 = a.J.r[M + i];
   }
   double* sv = sm.sv + tid;
 #pragma unroll
@@ -719,19 +788,15 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute
   if (tid < ti.np) {
     const size_t g = (size_t)ti.pt0 + tid;
     const double t0 = sm.sw[tid], t1 = sm.sw[TILE + tid], t2 = sm.sw[2 * TILE + tid];
-    const double h0 = a.hinv[g], h1 = a.hinv[P + g], h2 = a.hinv[2 * P + g], h3 = a.hinv[3 * P + g],
-                 h4 = a.hinv[4 * P + g], h5 = a.hinv[5 * P + g];
     // y_p = hinv (E'r - E'F y_c) = w - hinv t ;  step_p = -y_p
-    const double y0 = a.w[g] - (h0 * t0 + h1 * t1 + h2 * t2);
-    const double y1 = a.w[P + g] - (h1 * t0 + h3 * t1 + h4 * t2);
-    const double y2 = a.w[2 * P + g] - (h2 * t0 + h4 * t1 + h5 * t2);
+    const double y0 = wp[0] - (hp[0] * t0 + hp[1] * t1 + hp[2] * t2);
+    const double y1 = wp[1] - (hp[1] * t0 + hp[3] * t1 + hp[4] * t2);
+    const double y2 = wp[2] - (hp[2] * t0 + hp[4] * t1 + hp[5] * t2);
     sm.sw[tid] = y0; sm.sw[TILE + tid] = y1; sm.sw[2 * TILE + tid] = y2;
-    const double* sp = a.scale_p + 3 * g;
-    const double* X = a.X + 3 * g;
-    const double d0 = -y0 * sp[0], d1 = -y1 * sp[1], d2 = -y2 * sp[2];
-    const double c0 = X[0] + d0, c1 = X[1] + d1, c2 = X[2] + d2;
+    const double d0 = -y0 * spp[0], d1 = -y1 * spp[1], d2 = -y2 * spp[2];
+    const double c0 = Xp[0] + d0, c1 = Xp[1] + d1, c2 = Xp[2] + d2;
     a.Xc[3 * g] = c0; a.Xc[3 * g + 1] = c1; a.Xc[3 * g + 2] = c2;
-    const double e0 = X[0] - c0, e1 = X[1] - c1, e2 = X[2] - c2;
+    const double e0 = Xp[0] - c0, e1 = Xp[1] - c1, e2 = Xp[2] - c2;
     dx2 = e0 * e0 + e1 * e1 + e2 * e2;
     xc2 = c0 * c0 + c1 * c1 + c2 * c2;
   }

@@ -43,6 +43,20 @@ __global__ void k_fill(double* p, double v, size_t n) {
   if (i < n) p[i] = v;
 }
 
+// dst[i] (+)= sum over replicas of src[r][i]; the replicas are zeroed for the next use
+__global__ void k_fold_replicas(double* dst, double* rep, size_t n, size_t stride, int nrep, int accumulate,
+                                const int* skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = accumulate ? dst[i] : 0.0;
+  for (int r = 0; r < nrep; ++r) {
+    s += rep[(size_t)r * stride + i];
+    rep[(size_t)r * stride + i] = 0.0;
+  }
+  dst[i] = s;
+}
+
 // sum of squares of a vector (grid-stride), atomically added to *out
 __global__ void __launch_bounds__(256) k_sqnorm(const double* v, size_t n, double* out) {
   __shared__ double sred[32];

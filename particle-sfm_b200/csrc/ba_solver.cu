@@ -74,6 +74,7 @@ struct psfm_ba_solver {
   size_t jc_rows = 0, jk_rows = 0;
   // reduced system / PCG
   DBuf<double> d_lin, d_prep, d_step, d_rep, d_gmax, d_x2, d_Dc2, d_Minv, d_rhs, d_x, d_rv, d_p, d_z, d_y, d_zero;
+  DBuf<double> d_camrep, d_yrep;   // [NREP] replicas of the per-image accumulators (see ba_kernels.cuh)
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   cudaStream_t stream = nullptr;
@@ -232,6 +233,8 @@ void alloc_work(psfm_ba_solver* S) {
   S->d_Dc2.alloc(NS); S->d_Minv.alloc(9 * (size_t)S->NB); S->d_rhs.alloc(NS);
   S->d_x.alloc(NS); S->d_rv.alloc(NS); S->d_p.alloc(NS); S->d_z.alloc(NS); S->d_y.alloc(NS); S->d_zero.alloc(NS);
   S->d_zero.zero(S->stream);
+  S->d_camrep.alloc((size_t)NREP * F * NVL); S->d_camrep.zero(S->stream);
+  S->d_yrep.alloc((size_t)NREP * NS); S->d_yrep.zero(S->stream);
   S->d_pcg.alloc(1);
   PSFM_CUDA(cudaMallocHost((void**)&S->hs, sizeof(HostScalars)));
   memset(S->hs, 0, sizeof(HostScalars));
@@ -365,6 +368,11 @@ void d2h(psfm_ba_solver* S, T* dst, const T* src, size_t n) {
   PSFM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, S->stream));
 }
 
+void fold_replicas(psfm_ba_solver* S, double* dst, double* rep, size_t n, const int* skip_flag) {
+  k_fold_replicas<<<(unsigned)((n + 255) / 256), 256, 0, S->stream>>>(dst, rep, n, n, NREP, 0, skip_flag);
+  PSFM_LAUNCH_CHECK();
+}
+
 // Jacobian sweep at the current state (r, J, E'E, E'r, F'F blocks, F'r, cost)
 void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
   S->d_lin.zero(S->stream);
@@ -375,12 +383,13 @@ void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
   a.intr = c.intr;
   a.J = jac_of(S);
   a.hpp = S->d_hpp.p; a.gp = S->d_gp.p; a.wk = S->d_wk.p;
-  a.acc_cam = S->d_lin.p; a.acc_intr = S->d_lin.p + (size_t)S->F * NVL;
+  a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL; a.acc_intr = S->d_lin.p + (size_t)S->F * NVL;
   a.acc_cost = S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
   PSFM_TILE_LAUNCH(k_linearize, 18, S, c.rot, a);
   if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_lin.push_back({e0, e1}); }
+  fold_replicas(S, S->d_lin.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr);
   dist::allreduce_sum(S->d_lin.p, S->d_lin.n, S->stream);
 }
 
@@ -411,8 +420,9 @@ void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius) {
   S->d_prep.zero(S->stream);
   do_point_blocks(S, c, radius);
   PrepArgs a;
-  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.w = S->d_w.p; a.acc_cam = S->d_prep.p;
+  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.w = S->d_w.p; a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL;
   PSFM_TILE_LAUNCH(k_schur_prep, 18, S, c.rot, a);
+  fold_replicas(S, S->d_prep.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr);
   dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
   CamFinArgs f;
   f.lin_cam = S->d_lin.p; f.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
@@ -425,12 +435,13 @@ void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius) {
 
 void do_schur_product(psfm_ba_solver* S, const RunCfg& c, const double* x, bool timed) {
   SpArgs a;
-  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.x = x; a.y = S->d_y.p;
+  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.x = x; a.y = S->d_yrep.p; a.rep_stride = (size_t)S->NS;
   a.flag = &S->d_pcg.p->flag; a.intr = c.intr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
   PSFM_TILE_LAUNCH(k_schur_product, 6, S, c.rot, a);
   if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_sp.push_back({e0, e1}); }
+  fold_replicas(S, S->d_y.p, S->d_yrep.p, (size_t)S->NS, &S->d_pcg.p->flag);
   dist::allreduce_sum(S->d_y.p, S->d_y.n, S->stream);
 }
 
