@@ -30,7 +30,7 @@ def _worker(rank, world, port, q):
     own[distributed.owned_points(shard)] = 1
     dist.all_reduce(own)
     c, r, gc, gp = oracle.ba_evaluate(shard, o, num_threads=2)
-    tc, tg, tp = torch.tensor([c]), torch.from_numpy(gc.copy()), torch.from_numpy(gp.copy())
+    tc, tg, tp = torch.tensor([c], dtype=torch.float64), torch.from_numpy(gc.copy()), torch.from_numpy(gp.copy())
     dist.all_reduce(tc); dist.all_reduce(tg); dist.all_reduce(tp)
     c0, _, gc0, gp0 = oracle.ba_evaluate(prob, o, num_threads=2)
     # merge_points: every rank perturbs only its own points, the merge yields all of them
