@@ -207,49 +207,69 @@ class Reconstruction:
         return sorted(self.images.keys())
 
     def FilterObservationsWithNegativeDepth(self):
-        """base/reconstruction.cc:711-729: drop observations whose point lies behind the
-        camera (HasPointPositiveDepth uses depth >= eps)."""
+        """base/reconstruction.cc:711-729: delete every observation whose point is not in
+        front of the camera (HasPointPositiveDepth: P.row(2)·[X;1] >= eps).  As in
+        Reconstruction::DeleteObservation, a point whose track would drop below 2
+        observations is deleted with all its observations."""
         from .synthetic import qvec_to_rotmat
-        n = 0
         eps = np.finfo(np.float64).eps
+        track_len = {}
         for im in self.images.values():
+            if im.point3D_ids is not None:
+                for p in im.point3D_ids[im.point3D_ids >= 0]:
+                    track_len[int(p)] = track_len.get(int(p), 0) + 1
+        n = 0
+        for i in self.RegImageIds():
+            im = self.images[i]
             if im.point3D_ids is None:
                 continue
-            R = qvec_to_rotmat(im.qvec)
+            R = qvec_to_rotmat(im.qvec / np.linalg.norm(im.qvec))
             for j in np.nonzero(im.point3D_ids >= 0)[0]:
-                X = self.points3D[int(im.point3D_ids[j])].xyz
-                if R[2] @ X + im.tvec[2] < eps:
+                pid = int(im.point3D_ids[j])
+                if pid < 0 or pid not in self.points3D:
+                    continue
+                if R[2] @ self.points3D[pid].xyz + im.tvec[2] >= eps:
+                    continue
+                n += 1
+                if track_len.get(pid, 0) <= 2:          # DeletePoint3D
+                    for other in self.images.values():
+                        if other.point3D_ids is not None:
+                            other.point3D_ids[other.point3D_ids == pid] = -1
+                    self.points3D.pop(pid, None)
+                    track_len.pop(pid, None)
+                else:
                     im.point3D_ids[j] = -1
-                    n += 1
+                    track_len[pid] -= 1
         return n
 
     def Normalize(self, extent=10.0, p0=0.1, p1=0.9, use_images=True):
-        """base/reconstruction.cc:373-468: similarity re-gauge so that the p0..p1 percentile
-        box of the camera centres has diagonal `extent`, centred on their mean (the sort
-        keys are float32 as in the reference)."""
-        from .synthetic import camera_centres
+        """base/reconstruction.cc:373-468: per-axis sorted float32 camera-centre
+        coordinates, P0 = floor(p0 (n-1)), P1 = floor(p1 (n-1)) (0 and n-1 when n <= 3); the
+        box is [coords[P0], coords[P1]] per axis, the translation the mean of the sorted
+        coordinates in P0..P1; scale = extent / |box diagonal|."""
+        from .synthetic import camera_centres, qvec_to_rotmat
         ids = self.RegImageIds()
-        if len(ids) < 2:
+        if (use_images and len(ids) < 2) or (not use_images and len(self.points3D) < 2):
             return
         q = np.stack([self.images[i].qvec for i in ids])
+        q = q / np.linalg.norm(q, axis=1, keepdims=True)
         t = np.stack([self.images[i].tvec for i in ids])
-        cen = camera_centres(q / np.linalg.norm(q, axis=1, keepdims=True), t)
-        c32 = np.sort(cen.astype(np.float32), axis=0)
-        n = len(ids)
-        i0 = int(round(p0 * (n - 1))) if n > 3 else 0
-        i1 = int(round(p1 * (n - 1))) if n > 3 else n - 1
-        lo, hi = c32[i0].astype(np.float64), c32[i1].astype(np.float64)
-        sel = np.all((cen.astype(np.float32) >= c32[i0]) & (cen.astype(np.float32) <= c32[i1]), axis=1)
-        mean = cen[sel].mean(0) if sel.any() else cen.mean(0)
+        cen = camera_centres(q, t)
+        coords = cen if use_images else np.stack([p.xyz for p in self.points3D.values()])
+        cs = np.sort(coords.astype(np.float32), axis=0)
+        n = cs.shape[0]
+        P0 = int(p0 * (n - 1)) if n > 3 else 0
+        P1 = int(p1 * (n - 1)) if n > 3 else n - 1
+        lo, hi = cs[P0].astype(np.float64), cs[P1].astype(np.float64)
+        mean = cs[P0:P1 + 1].astype(np.float64).sum(0) / (P1 - P0 + 1)
         old_extent = np.linalg.norm(hi - lo)
         scale = 1.0 if old_extent < np.finfo(np.float64).eps else extent / old_extent
-        from .synthetic import qvec_to_rotmat
+        R = qvec_to_rotmat(q)
         for k, i in enumerate(ids):
-            im = self.images[i]
-            R = qvec_to_rotmat(im.qvec / np.linalg.norm(im.qvec))
-            im.tvec = -R @ (scale * (cen[k] - mean))
+            self.images[i].tvec = R[k] @ (-(cen[k] - mean) * scale)
         for p in self.points3D.values():
-            p.xyz = scale * (p.xyz - mean)
+            p.xyz = (p.xyz - mean) * scale
+        return mean, scale
 
 
 def flatten(reconstruction, config):

@@ -8,8 +8,11 @@
 //   rules from :326-447 / :500-544, solver selection rule :276-286, option policy
 //   controllers/global_mapper.cc:41-71.
 // There is no CPU path: every numeric step below is a kernel launch.
+#include <parallel/algorithm>
+
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -104,7 +107,28 @@ double now_s() {
 
 // ---------------------------------------------------------------- structure
 
+struct PhaseTimer {
+  bool on;
+  double t;
+  explicit PhaseTimer() : on(getenv("PSFM_TIMING") != nullptr), t(now_s()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const double n = now_s();
+    fprintf(stderr, "[psfm timing] %-28s %8.2f ms\n", what, 1e3 * (n - t));
+    t = n;
+  }
+};
+
+struct ObsKey {
+  unsigned long long key;   // (internal point << 32) | image
+  int idx;                  // caller's observation index (tie break -> deterministic order)
+  bool operator<(const ObsKey& o) const { return key != o.key ? key < o.key : idx < o.idx; }
+};
+
+// Host-side flattening of the problem into tiles (multi-threaded: this is part of the
+// end-to-end time of psfm_ba_solve).
 int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
+  PhaseTimer tm;
   const int F = pb->num_images, Pt = pb->num_points, M = pb->num_observations, C = pb->num_cameras;
   if (F <= 0 || C <= 0 || Pt < 0 || M < 0) { set_error("psfm_ba_create: bad sizes"); return PSFM_ERR_INVALID; }
   S->F = F; S->P_total = Pt; S->M = M; S->C = C; S->NS = 6 * F + 3 * C; S->NB = 2 * F + C;
@@ -119,14 +143,19 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
 
   // points: observation counts and first image
   std::vector<int> cnt(Pt, 0), min_img(Pt, F);
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
   for (int i = 0; i < M; ++i) {
     const int im = pb->obs_image[i], pt = pb->obs_point[i];
-    if (im < 0 || im >= F || pt < 0 || pt >= Pt) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
-    cnt[pt]++;
-    if (im < min_img[pt]) min_img[pt] = im;
+    if (im < 0 || im >= F || pt < 0 || pt >= Pt) { bad = 1; continue; }
+    __atomic_fetch_add(&cnt[pt], 1, __ATOMIC_RELAXED);
+    int cur = __atomic_load_n(&min_img[pt], __ATOMIC_RELAXED);
+    while (im < cur && !__atomic_compare_exchange_n(&min_img[pt], &cur, im, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     S->img_has_obs[im] = 1;
-    S->cam_has_obs[S->image_camera[im]] = 1;
   }
+  if (bad) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
+  for (int i = 0; i < F; ++i) if (S->img_has_obs[i]) S->cam_has_obs[S->image_camera[i]] = 1;
+  tm.mark("count observations");
   // internal point order: observed points by (first image, id) — keeps the image window
   // of a tile narrow for video tracks (few image segments per tile)
   std::vector<int> bucket(F + 2, 0);
@@ -143,27 +172,28 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   S->maxL = maxL;
   if (maxL > 1024) { set_error("a track with more than 1024 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
   S->tile = maxL <= 256 ? 256 : (maxL <= 512 ? 512 : 1024);
-  // sort observations by (internal point, image): counting sort by image, then stable by point
-  std::vector<int> by_img(M);
-  {
-    std::vector<int> ib(F + 1, 0);
-    for (int i = 0; i < M; ++i) ib[pb->obs_image[i] + 1]++;
-    for (int f = 0; f < F; ++f) ib[f + 1] += ib[f];
-    for (int i = 0; i < M; ++i) by_img[ib[pb->obs_image[i]]++] = i;
+  tm.mark("order points");
+  // sort observations by (internal point, image)
+  std::vector<ObsKey> keys(M);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < M; ++i) {
+    keys[i].key = ((unsigned long long)(unsigned)pt_new[pb->obs_point[i]] << 32) | (unsigned)pb->obs_image[i];
+    keys[i].idx = i;
   }
+  __gnu_parallel::sort(keys.begin(), keys.end());
+  tm.mark("sort observations");
   S->obs_orig.assign(M, 0);
-  {
-    std::vector<int> fill(pt_ptr.begin(), pt_ptr.end() - 1);
-    for (int j = 0; j < M; ++j) { const int i = by_img[j]; S->obs_orig[fill[pt_new[pb->obs_point[i]]]++] = i; }
-  }
   std::vector<int> obs_img(M), obs_pt(M);
   std::vector<double2> obs_xy(M);
+#pragma omp parallel for schedule(static)
   for (int j = 0; j < M; ++j) {
-    const int i = S->obs_orig[j];
-    obs_img[j] = pb->obs_image[i];
-    obs_pt[j] = pt_new[pb->obs_point[i]];
+    const int i = keys[j].idx;
+    S->obs_orig[j] = i;
+    obs_img[j] = (int)(keys[j].key & 0xffffffffu);
+    obs_pt[j] = (int)(keys[j].key >> 32);
     obs_xy[j] = make_double2(pb->obs_xy[2 * (size_t)i], pb->obs_xy[2 * (size_t)i + 1]);
   }
+  tm.mark("gather observations");
   // tiles: whole points, <= tile observations
   const int TILE = S->tile;
   std::vector<int> tile_start, tile_pt;
@@ -179,29 +209,38 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   }
   const int T = (int)tile_start.size() - 1;
   S->T = T;
-  // per tile: image order + segments
-  std::vector<unsigned short> tile_perm(M), cseg_off;
-  std::vector<int> cseg_ptr(T + 1, 0), cseg_img;
-  cseg_off.reserve(M / 4 + 16); cseg_img.reserve(M / 4 + 16);
+  // per tile: image order + segments (two passes: count segments, then fill)
+  std::vector<unsigned short> tile_perm(M);
+  std::vector<int> cseg_ptr(T + 1, 0);
+#pragma omp parallel
   {
     std::vector<int> cntf(F + 1, 0);
+#pragma omp for schedule(static)
     for (int t = 0; t < T; ++t) {
       const int b = tile_start[t], n = tile_start[t + 1] - b;
-      int lo = F, hi = -1;
+      int lo = F, hi = -1, ns = 0;
       for (int e = 0; e < n; ++e) { const int im = obs_img[b + e]; lo = std::min(lo, im); hi = std::max(hi, im); cntf[im]++; }
       int run = 0;
-      for (int f = lo; f <= hi; ++f) {
-        const int c = cntf[f];
-        if (c > 0) { cseg_img.push_back(f); cseg_off.push_back((unsigned short)run); }
-        cntf[f] = run;
-        run += c;
-      }
+      for (int f = lo; f <= hi; ++f) { const int c = cntf[f]; if (c > 0) ++ns; cntf[f] = run; run += c; }
       for (int e = 0; e < n; ++e) tile_perm[b + cntf[obs_img[b + e]]++] = (unsigned short)e;
       for (int f = lo; f <= hi; ++f) cntf[f] = 0;
-      cseg_ptr[t + 1] = (int)cseg_img.size();
+      cseg_ptr[t + 1] = ns;
     }
   }
-  S->nseg = (int)cseg_img.size();
+  for (int t = 0; t < T; ++t) cseg_ptr[t + 1] += cseg_ptr[t];
+  S->nseg = cseg_ptr[T];
+  std::vector<unsigned short> cseg_off(S->nseg);
+  std::vector<int> cseg_img(S->nseg);
+#pragma omp parallel for schedule(static)
+  for (int t = 0; t < T; ++t) {
+    const int b = tile_start[t], n = tile_start[t + 1] - b;
+    int s = cseg_ptr[t], prev = -1;
+    for (int e = 0; e < n; ++e) {
+      const int im = obs_img[b + tile_perm[b + e]];
+      if (im != prev) { cseg_img[s] = im; cseg_off[s] = (unsigned short)e; ++s; prev = im; }
+    }
+  }
+  tm.mark("tiles and image segments");
   // upload
   cudaStream_t st = S->stream;
   S->d_tile_start.alloc(T + 1); S->d_tile_start.upload(tile_start.data(), T + 1, st);
@@ -216,6 +255,7 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   S->d_cseg_off.alloc(S->nseg); S->d_cseg_off.upload(cseg_off.data(), S->nseg, st);
   S->d_img_cam.alloc(F); S->d_img_cam.upload(S->image_camera.data(), F, st);
   PSFM_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+  tm.mark("upload structure");
   return PSFM_OK;
 }
 
@@ -836,8 +876,10 @@ extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
     S->h_tvec.assign(pb->tvec, pb->tvec + 3 * (size_t)S->F);
     S->h_xyz.assign(pb->xyz, pb->xyz + 3 * (size_t)S->P_total);
     S->h_K.assign(pb->cam_params, pb->cam_params + 3 * (size_t)S->C);
+    PhaseTimer tm;
     alloc_work(S);
     PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    tm.mark("allocate work buffers");
   } catch (const CudaFail& f) {
     delete S;
     return f.code;
