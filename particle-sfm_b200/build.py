@@ -21,7 +21,7 @@ BUILD = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp", "-ccbin", CXX]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", CXX]
 
 # (source, extra flags).  traj_solver.cu: -fmad=false so that its iterates are
 # bit-identical to the oracle compiled with -ffp-contract=off.
@@ -60,7 +60,7 @@ def build_library(force=False, verbose=False):
             print("[build]", " ".join(cmd), flush=True)
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl", "-lgomp"]
+        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl"]
         print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     return LIB

@@ -8,8 +8,6 @@
 //   rules from :326-447 / :500-544, solver selection rule :276-286, option policy
 //   controllers/global_mapper.cc:41-71.
 // There is no CPU path: every numeric step below is a kernel launch.
-#include <parallel/algorithm>
-
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -17,6 +15,7 @@
 #include <vector>
 
 #include "ba_small_kernels.cuh"
+#include "ba_structure.cuh"
 #include "dist.cuh"
 
 namespace psfm {
@@ -55,8 +54,17 @@ struct HostScalars {   // pinned
 using namespace psfm;
 using namespace psfm::ba;
 
+struct StreamHolder {   // declared first in the solver => destroyed last (after every DBuf)
+  cudaStream_t s = nullptr;
+  ~StreamHolder() {
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  }
+};
+
 struct psfm_ba_solver {
+  StreamHolder sh;
   int F = 0, P_total = 0, P = 0, M = 0, C = 0, NS = 0, NB = 0, T = 0, nseg = 0, tile = 256, maxL = 0;
+  int cap_ns = 1, cap_np = 1;
   // host structure / config
   std::vector<int> pt_orig;      // internal point -> caller's point id
   std::vector<int> obs_orig;     // sorted observation -> caller's observation index
@@ -66,7 +74,8 @@ struct psfm_ba_solver {
   std::vector<double> h_qvec, h_tvec, h_xyz, h_K;
   // device structure
   DBuf<int> d_tile_start, d_tile_pt, d_pt_ptr, d_obs_img, d_obs_pt, d_cseg_ptr, d_cseg_img, d_img_cam;
-  DBuf<unsigned short> d_tile_perm, d_cseg_off;
+  DBuf<unsigned short> d_tile_perm, d_cseg_off, d_obs_lseg, d_obs_lpt;
+  DBuf<int> d_obs_orig;
   DBuf<double2> d_obs_xy;
   DBuf<unsigned char> d_active;
   // device state
@@ -94,8 +103,8 @@ struct psfm_ba_solver {
     return t;
   }
   ~psfm_ba_solver() {
+    if (stream) cudaStreamSynchronize(stream);
     if (hs) cudaFreeHost(hs);
-    if (stream) cudaStreamDestroy(stream);
   }
 };
 
@@ -119,14 +128,15 @@ struct PhaseTimer {
   }
 };
 
-struct ObsKey {
-  unsigned long long key;   // (internal point << 32) | image
-  int idx;                  // caller's observation index (tie break -> deterministic order)
-  bool operator<(const ObsKey& o) const { return key != o.key ? key < o.key : idx < o.idx; }
-};
+template <typename T>
+void d2h_sync(cudaStream_t st, T* dst, const T* src, size_t n) {
+  if (n) PSFM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaStreamSynchronize(st));
+}
 
-// Host-side flattening of the problem into tiles (multi-threaded: this is part of the
-// end-to-end time of psfm_ba_solve).
+inline unsigned grid_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
+// Device-side flattening of the problem into tiles (ba_structure.cuh).
 int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   PhaseTimer tm;
   const int F = pb->num_images, Pt = pb->num_points, M = pb->num_observations, C = pb->num_cameras;
@@ -140,142 +150,155 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   if (pb->tvec_constant_mask) S->tvec_mask.assign(pb->tvec_constant_mask, pb->tvec_constant_mask + F);
   if (pb->camera_constant) S->camera_constant.assign(pb->camera_constant, pb->camera_constant + C);
   S->img_has_obs.assign(F, 0); S->cam_has_obs.assign(C, 0);
+  cudaStream_t st = S->stream;
+  S->d_img_cam.alloc(F, st); S->d_img_cam.upload(S->image_camera.data(), F, st);
 
-  // points: observation counts and first image
-  std::vector<int> cnt(Pt, 0), min_img(Pt, F);
-  int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-  for (int i = 0; i < M; ++i) {
-    const int im = pb->obs_image[i], pt = pb->obs_point[i];
-    if (im < 0 || im >= F || pt < 0 || pt >= Pt) { bad = 1; continue; }
-    __atomic_fetch_add(&cnt[pt], 1, __ATOMIC_RELAXED);
-    int cur = __atomic_load_n(&min_img[pt], __ATOMIC_RELAXED);
-    while (im < cur && !__atomic_compare_exchange_n(&min_img[pt], &cur, im, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-    S->img_has_obs[im] = 1;
+  // raw observations -> device
+  DBuf<int> in_img, in_pt, cnt, min_img, order, keys32, keys32_out, pt_new, cnt_sorted, idx, idx_out, tile_ns, bad;
+  DBuf<double2> in_xy;
+  DBuf<unsigned long long> keys, keys_out;
+  DBuf<unsigned char> has_obs, tmp;
+  in_img.alloc(M, st); in_pt.alloc(M, st); in_xy.alloc(M, st);
+  in_img.upload(pb->obs_image, M, st); in_pt.upload(pb->obs_point, M, st);
+  in_xy.upload(reinterpret_cast<const double2*>(pb->obs_xy), M, st);
+  cnt.alloc(Pt, st); min_img.alloc(Pt, st); has_obs.alloc(F, st); bad.alloc(1, st);
+  has_obs.zero(st); bad.zero(st);
+  if (Pt) { k_st_init<<<grid_for(Pt), 256, 0, st>>>(cnt.p, min_img.p, Pt, F); PSFM_LAUNCH_CHECK(); }
+  if (M) { k_st_count<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, M, F, Pt, cnt.p, min_img.p, has_obs.p, bad.p); PSFM_LAUNCH_CHECK(); }
+  // internal point order: observed points by (first image, id); unobserved (key F) last
+  order.alloc(Pt, st); keys32.alloc(Pt, st); keys32_out.alloc(Pt, st); idx.alloc(std::max(Pt, M), st); idx_out.alloc(std::max(Pt, M), st);
+  pt_new.alloc(Pt, st); cnt_sorted.alloc((size_t)Pt + 1, st);
+  int fbits = 1; while ((1 << fbits) <= F) ++fbits;
+  size_t tmp_bytes = 0, need = 0;
+  if (Pt) {
+    k_st_iota<<<grid_for(Pt), 256, 0, st>>>(idx.p, Pt); PSFM_LAUNCH_CHECK();
+    cub::DeviceRadixSort::SortPairs(nullptr, need, min_img.p, keys32_out.p, idx.p, order.p, Pt, 0, fbits, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+    cub::DeviceScan::ExclusiveSum(nullptr, need, cnt_sorted.p, cnt_sorted.p, Pt + 1, st);
+    tmp_bytes = std::max(tmp_bytes, need);
   }
-  if (bad) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
-  for (int i = 0; i < F; ++i) if (S->img_has_obs[i]) S->cam_has_obs[S->image_camera[i]] = 1;
-  tm.mark("count observations");
-  // internal point order: observed points by (first image, id) — keeps the image window
-  // of a tile narrow for video tracks (few image segments per tile)
-  std::vector<int> bucket(F + 2, 0);
-  int P = 0;
-  for (int p = 0; p < Pt; ++p) if (cnt[p] > 0) { bucket[min_img[p] + 1]++; ++P; }
-  for (int f = 0; f < F; ++f) bucket[f + 1] += bucket[f];
-  S->P = P;
-  S->pt_orig.assign(P, 0);
-  std::vector<int> pt_new(Pt, -1);
-  for (int p = 0; p < Pt; ++p) if (cnt[p] > 0) { const int id = bucket[min_img[p]]++; S->pt_orig[id] = p; pt_new[p] = id; }
-  std::vector<int> pt_ptr(P + 1, 0);
-  int maxL = 0;
-  for (int id = 0; id < P; ++id) { pt_ptr[id + 1] = pt_ptr[id] + cnt[S->pt_orig[id]]; maxL = std::max(maxL, cnt[S->pt_orig[id]]); }
-  S->maxL = maxL;
+  int pbits = 1; while ((1ll << pbits) <= (long long)Pt) ++pbits;
+  keys.alloc(M, st); keys_out.alloc(M, st);
+  if (M) {
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys.p, keys_out.p, idx.p, idx_out.p, M, 0, 32 + pbits, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+  }
+  tmp.alloc(tmp_bytes + 256, st);
+  std::vector<int> h_cnt(Pt);
+  if (Pt) {
+    need = tmp_bytes + 256;
+    cub::DeviceRadixSort::SortPairs(tmp.p, need, min_img.p, keys32_out.p, idx.p, order.p, Pt, 0, fbits, st);
+    k_st_rank<<<grid_for(Pt), 256, 0, st>>>(order.p, cnt.p, Pt, pt_new.p, cnt_sorted.p); PSFM_LAUNCH_CHECK();
+  }
+  PSFM_CUDA(cudaMemsetAsync(cnt_sorted.p + Pt, 0, sizeof(int), st));
+  // host needs: validity, observed flags, point order, counts
+  int h_bad = 0;
+  std::vector<unsigned char> h_has(F);
+  std::vector<int> h_order(Pt), h_cs(Pt);
+  PSFM_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaMemcpyAsync(h_has.data(), has_obs.p, F, cudaMemcpyDeviceToHost, st));
+  if (Pt) {
+    PSFM_CUDA(cudaMemcpyAsync(h_order.data(), order.p, sizeof(int) * Pt, cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaMemcpyAsync(h_cs.data(), cnt_sorted.p, sizeof(int) * Pt, cudaMemcpyDeviceToHost, st));
+  }
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  if (h_bad) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
+  tm.mark("upload + count + order points");
+  for (int i = 0; i < F; ++i) if (h_has[i]) { S->img_has_obs[i] = 1; S->cam_has_obs[S->image_camera[i]] = 1; }
+  int P = 0, maxL = 0;
+  while (P < Pt && h_cs[P] > 0) ++P;           // observed points come first
+  for (int j = 0; j < P; ++j) maxL = std::max(maxL, h_cs[j]);
+  S->P = P; S->maxL = maxL;
+  S->pt_orig.assign(h_order.begin(), h_order.begin() + P);
   if (maxL > 1024) { set_error("a track with more than 1024 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
   S->tile = maxL <= 256 ? 256 : (maxL <= 512 ? 512 : 1024);
-  tm.mark("order points");
-  // sort observations by (internal point, image)
-  std::vector<ObsKey> keys(M);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < M; ++i) {
-    keys[i].key = ((unsigned long long)(unsigned)pt_new[pb->obs_point[i]] << 32) | (unsigned)pb->obs_image[i];
-    keys[i].idx = i;
-  }
-  __gnu_parallel::sort(keys.begin(), keys.end());
-  tm.mark("sort observations");
-  S->obs_orig.assign(M, 0);
-  std::vector<int> obs_img(M), obs_pt(M);
-  std::vector<double2> obs_xy(M);
-#pragma omp parallel for schedule(static)
-  for (int j = 0; j < M; ++j) {
-    const int i = keys[j].idx;
-    S->obs_orig[j] = i;
-    obs_img[j] = (int)(keys[j].key & 0xffffffffu);
-    obs_pt[j] = (int)(keys[j].key >> 32);
-    obs_xy[j] = make_double2(pb->obs_xy[2 * (size_t)i], pb->obs_xy[2 * (size_t)i + 1]);
-  }
-  tm.mark("gather observations");
-  // tiles: whole points, <= tile observations
+  // tiles: whole points, <= tile observations (greedy, host: P iterations)
   const int TILE = S->tile;
-  std::vector<int> tile_start, tile_pt;
+  std::vector<int> pt_ptr(P + 1, 0), tile_start, tile_pt;
   tile_start.push_back(0); tile_pt.push_back(0);
   {
-    int cur = 0;
+    int cur = 0, np_cur = 0, cap_np = 1;
     for (int id = 0; id < P; ++id) {
-      const int L = pt_ptr[id + 1] - pt_ptr[id];
-      if (cur + L > TILE) { tile_start.push_back(pt_ptr[id]); tile_pt.push_back(id); cur = 0; }
-      cur += L;
+      const int L = h_cs[id];
+      pt_ptr[id + 1] = pt_ptr[id] + L;
+      if (cur + L > TILE) { tile_start.push_back(pt_ptr[id]); tile_pt.push_back(id); cap_np = std::max(cap_np, np_cur); cur = 0; np_cur = 0; }
+      cur += L; ++np_cur;
     }
+    cap_np = std::max(cap_np, np_cur);
     if (P > 0) { tile_start.push_back(M); tile_pt.push_back(P); }
+    S->cap_np = cap_np;
   }
   const int T = (int)tile_start.size() - 1;
   S->T = T;
-  // per tile: image order + segments (two passes: count segments, then fill)
-  std::vector<unsigned short> tile_perm(M);
-  std::vector<int> cseg_ptr(T + 1, 0);
-#pragma omp parallel
+  S->d_tile_start.alloc(T + 1, st); S->d_tile_start.upload(tile_start.data(), T + 1, st);
+  S->d_tile_pt.alloc(T + 1, st); S->d_tile_pt.upload(tile_pt.data(), T + 1, st);
+  S->d_pt_ptr.alloc(P + 1, st); S->d_pt_ptr.upload(pt_ptr.data(), P + 1, st);
+  tm.mark("tiles (host greedy)");
+  // sort observations by (internal point, image); radix sort is stable => ties keep input order
+  S->d_obs_img.alloc(M, st); S->d_obs_pt.alloc(M, st); S->d_obs_xy.alloc(M, st); S->d_obs_orig.alloc(M, st);
+  S->d_tile_perm.alloc(M, st); S->d_obs_lseg.alloc(M, st); S->d_obs_lpt.alloc(M, st);
+  S->d_cseg_ptr.alloc((size_t)T + 1, st);
+  if (M) {
+    k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
+    need = tmp_bytes + 256;
+    cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, idx.p, S->d_obs_orig.p, M, 0, 32 + pbits, st);
+    k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy.p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
+    PSFM_LAUNCH_CHECK();
+  }
+  // per tile: image order, local indices, segments
+  tile_ns.alloc((size_t)T + 1, st);
+  PSFM_CUDA(cudaMemsetAsync(tile_ns.p, 0, sizeof(int) * ((size_t)T + 1), st));
+  if (T) {
+    if (TILE == 256) k_st_tile_order<256><<<T, 256, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
+    else if (TILE == 512) k_st_tile_order<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
+    else k_st_tile_order<1024><<<T, 1024, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
+    PSFM_LAUNCH_CHECK();
+  }
   {
-    std::vector<int> cntf(F + 1, 0);
-#pragma omp for schedule(static)
-    for (int t = 0; t < T; ++t) {
-      const int b = tile_start[t], n = tile_start[t + 1] - b;
-      int lo = F, hi = -1, ns = 0;
-      for (int e = 0; e < n; ++e) { const int im = obs_img[b + e]; lo = std::min(lo, im); hi = std::max(hi, im); cntf[im]++; }
-      int run = 0;
-      for (int f = lo; f <= hi; ++f) { const int c = cntf[f]; if (c > 0) ++ns; cntf[f] = run; run += c; }
-      for (int e = 0; e < n; ++e) tile_perm[b + cntf[obs_img[b + e]]++] = (unsigned short)e;
-      for (int f = lo; f <= hi; ++f) cntf[f] = 0;
-      cseg_ptr[t + 1] = ns;
-    }
+    need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, tile_ns.p, S->d_cseg_ptr.p, T + 1, st);
+    DBuf<unsigned char> tmp2; tmp2.alloc(need + 256, st);
+    cub::DeviceScan::ExclusiveSum(tmp2.p, need, tile_ns.p, S->d_cseg_ptr.p, T + 1, st);
+    DBuf<int> mx; mx.alloc(1, st);
+    size_t need2 = 0;
+    cub::DeviceReduce::Max(nullptr, need2, tile_ns.p, mx.p, T + 1, st);
+    DBuf<unsigned char> tmp3; tmp3.alloc(need2 + 256, st);
+    cub::DeviceReduce::Max(tmp3.p, need2, tile_ns.p, mx.p, T + 1, st);
+    int h_nseg = 0, h_mx = 1;
+    PSFM_CUDA(cudaMemcpyAsync(&h_nseg, S->d_cseg_ptr.p + T, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaMemcpyAsync(&h_mx, mx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->nseg = h_nseg; S->cap_ns = std::max(1, h_mx);
   }
-  for (int t = 0; t < T; ++t) cseg_ptr[t + 1] += cseg_ptr[t];
-  S->nseg = cseg_ptr[T];
-  std::vector<unsigned short> cseg_off(S->nseg);
-  std::vector<int> cseg_img(S->nseg);
-#pragma omp parallel for schedule(static)
-  for (int t = 0; t < T; ++t) {
-    const int b = tile_start[t], n = tile_start[t + 1] - b;
-    int s = cseg_ptr[t], prev = -1;
-    for (int e = 0; e < n; ++e) {
-      const int im = obs_img[b + tile_perm[b + e]];
-      if (im != prev) { cseg_img[s] = im; cseg_off[s] = (unsigned short)e; ++s; prev = im; }
-    }
+  S->d_cseg_img.alloc(S->nseg, st); S->d_cseg_off.alloc(S->nseg, st);
+  if (T) {
+    if (TILE == 256) k_st_tile_segments<256><<<T, 256, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
+    else if (TILE == 512) k_st_tile_segments<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
+    else k_st_tile_segments<1024><<<T, 1024, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
+    PSFM_LAUNCH_CHECK();
   }
-  tm.mark("tiles and image segments");
-  // upload
-  cudaStream_t st = S->stream;
-  S->d_tile_start.alloc(T + 1); S->d_tile_start.upload(tile_start.data(), T + 1, st);
-  S->d_tile_pt.alloc(T + 1); S->d_tile_pt.upload(tile_pt.data(), T + 1, st);
-  S->d_pt_ptr.alloc(P + 1); S->d_pt_ptr.upload(pt_ptr.data(), P + 1, st);
-  S->d_obs_img.alloc(M); S->d_obs_img.upload(obs_img.data(), M, st);
-  S->d_obs_pt.alloc(M); S->d_obs_pt.upload(obs_pt.data(), M, st);
-  S->d_obs_xy.alloc(M); S->d_obs_xy.upload(obs_xy.data(), M, st);
-  S->d_tile_perm.alloc(M); S->d_tile_perm.upload(tile_perm.data(), M, st);
-  S->d_cseg_ptr.alloc(T + 1); S->d_cseg_ptr.upload(cseg_ptr.data(), T + 1, st);
-  S->d_cseg_img.alloc(S->nseg); S->d_cseg_img.upload(cseg_img.data(), S->nseg, st);
-  S->d_cseg_off.alloc(S->nseg); S->d_cseg_off.upload(cseg_off.data(), S->nseg, st);
-  S->d_img_cam.alloc(F); S->d_img_cam.upload(S->image_camera.data(), F, st);
-  PSFM_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
-  tm.mark("upload structure");
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  tm.mark("sort + tile order (device)");
   return PSFM_OK;
 }
 
 void alloc_work(psfm_ba_solver* S) {
   const size_t M = S->M, P = S->P, F = S->F, C = S->C, NS = S->NS;
-  S->d_active.alloc(NS);
-  for (int k = 0; k < 2; ++k) { S->d_pose[k].alloc(8 * F); S->d_X[k].alloc(3 * P); S->d_K[k].alloc(3 * C); }
-  S->d_r.alloc(2 * M); S->d_jp.alloc(6 * M);
+  S->d_active.alloc(NS, S->stream);
+  for (int k = 0; k < 2; ++k) { S->d_pose[k].alloc(8 * F, S->stream); S->d_X[k].alloc(3 * P, S->stream); S->d_K[k].alloc(3 * C, S->stream); }
+  S->d_r.alloc(2 * M, S->stream); S->d_jp.alloc(6 * M, S->stream);
   S->jc_rows = 0; S->jk_rows = 0;   // d_jc / d_jk sized on first run (depends on options)
-  S->d_hpp.alloc(6 * P); S->d_gp.alloc(3 * P); S->d_wk.alloc(9 * P); S->d_hinv.alloc(6 * P); S->d_w.alloc(3 * P);
-  S->d_scale_c.alloc(NS); S->d_scale_p.alloc(3 * P);
-  S->d_lin.alloc(F * NVL + C * NVI + 1);
-  S->d_prep.alloc(F * NVL + C * NVI + 1);
-  S->d_step.alloc(4); S->d_rep.alloc(2); S->d_gmax.alloc(1); S->d_x2.alloc(1);
-  S->d_Dc2.alloc(NS); S->d_Minv.alloc(9 * (size_t)S->NB); S->d_rhs.alloc(NS);
-  S->d_x.alloc(NS); S->d_rv.alloc(NS); S->d_p.alloc(NS); S->d_z.alloc(NS); S->d_y.alloc(NS); S->d_zero.alloc(NS);
+  S->d_hpp.alloc(6 * P, S->stream); S->d_gp.alloc(3 * P, S->stream); S->d_wk.alloc(9 * P, S->stream); S->d_hinv.alloc(6 * P, S->stream); S->d_w.alloc(3 * P, S->stream);
+  S->d_scale_c.alloc(NS, S->stream); S->d_scale_p.alloc(3 * P, S->stream);
+  S->d_lin.alloc(F * NVL + C * NVI + 1, S->stream);
+  S->d_prep.alloc(F * NVL + C * NVI + 1, S->stream);
+  S->d_step.alloc(4, S->stream); S->d_rep.alloc(2, S->stream); S->d_gmax.alloc(1, S->stream); S->d_x2.alloc(1, S->stream);
+  S->d_Dc2.alloc(NS, S->stream); S->d_Minv.alloc(9 * (size_t)S->NB, S->stream); S->d_rhs.alloc(NS, S->stream);
+  S->d_x.alloc(NS, S->stream); S->d_rv.alloc(NS, S->stream); S->d_p.alloc(NS, S->stream); S->d_z.alloc(NS, S->stream); S->d_y.alloc(NS, S->stream); S->d_zero.alloc(NS, S->stream);
   S->d_zero.zero(S->stream);
-  S->d_camrep.alloc((size_t)NREP * F * NVL); S->d_camrep.zero(S->stream);
-  S->d_yrep.alloc((size_t)NREP * NS); S->d_yrep.zero(S->stream);
-  S->d_pcg.alloc(1);
+  S->d_camrep.alloc((size_t)NREP * F * NVL, S->stream); S->d_camrep.zero(S->stream);
+  S->d_yrep.alloc((size_t)NREP * NS, S->stream); S->d_yrep.zero(S->stream);
+  S->d_pcg.alloc(1, S->stream);
   PSFM_CUDA(cudaMallocHost((void**)&S->hs, sizeof(HostScalars)));
   memset(S->hs, 0, sizeof(HostScalars));
 }
@@ -399,8 +422,8 @@ Jac jac_of(psfm_ba_solver* S) {
 
 void ensure_jac(psfm_ba_solver* S, const RunCfg& c) {
   const size_t rows = c.rot ? 12 : 6, krows = c.intr == 3 ? 4 : (c.intr == 1 ? 2 : 0);
-  if (S->jc_rows < rows || !S->d_jc.p) { S->d_jc.alloc(rows * (size_t)S->M); S->jc_rows = rows; }
-  if (S->jk_rows < krows || !S->d_jk.p) { S->d_jk.alloc(std::max<size_t>(krows, 1) * (size_t)S->M); S->jk_rows = krows; }
+  if (S->jc_rows < rows || !S->d_jc.p) { S->d_jc.alloc(rows * (size_t)S->M, S->stream); S->jc_rows = rows; }
+  if (S->jk_rows < krows || !S->d_jk.p) { S->d_jk.alloc(std::max<size_t>(krows, 1) * (size_t)S->M, S->stream); S->jk_rows = krows; }
 }
 
 template <typename T>
@@ -869,7 +892,8 @@ extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
   if (rc != PSFM_OK) return rc;
   psfm_ba_solver* S = new psfm_ba_solver();
   try {
-    PSFM_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+    PSFM_CUDA(cudaStreamCreateWithFlags(&S->sh.s, cudaStreamNonBlocking));
+    S->stream = S->sh.s;
     rc = build_structure(S, pb);
     if (rc != PSFM_OK) { delete S; return rc; }
     S->h_qvec.assign(pb->qvec, pb->qvec + 4 * (size_t)S->F);
@@ -949,6 +973,8 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
     do_linearize(S, c, false);
     const size_t F = S->F, C = S->C, M = S->M, P = S->P;
     std::vector<double> lin(S->d_lin.n), r(2 * M), gp(3 * P);
+    std::vector<int> obs_orig(M);
+    if (M) d2h(S, obs_orig.data(), S->d_obs_orig.p, M);
     d2h(S, lin.data(), S->d_lin.p, lin.size());
     if (M) d2h(S, r.data(), S->d_r.p, 2 * M);
     if (P) d2h(S, gp.data(), S->d_gp.p, 3 * P);
@@ -956,8 +982,8 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
     if (cost) *cost = lin[F * NVL + C * NVI];
     if (residuals)
       for (size_t j = 0; j < M; ++j) {
-        residuals[2 * (size_t)S->obs_orig[j]] = r[j];
-        residuals[2 * (size_t)S->obs_orig[j] + 1] = r[M + j];
+        residuals[2 * (size_t)obs_orig[j]] = r[j];
+        residuals[2 * (size_t)obs_orig[j] + 1] = r[M + j];
       }
     if (gradient_cam) {
       for (size_t i = 0; i < F; ++i)

@@ -5,6 +5,17 @@ namespace psfm {
 static thread_local std::string g_error;
 std::atomic<long long> g_launch_count{0};
 void set_error(const std::string& msg) { g_error = msg; }
+void keep_pool_memory() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
 }  // namespace psfm
 
 extern "C" const char* psfm_last_error(void) { return psfm::g_error.c_str(); }

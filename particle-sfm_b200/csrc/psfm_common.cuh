@@ -36,25 +36,42 @@ struct CudaFail {
     PSFM_CUDA(cudaGetLastError());           \
   } while (0)
 
-// RAII device buffer
+// RAII device buffer.  With a stream: stream-ordered allocation from the default memory
+// pool (cudaMallocAsync), whose release threshold psfm::keep_pool_memory() raises so that
+// create/destroy cycles of a solver re-use the cached blocks instead of paying cudaMalloc.
+void keep_pool_memory();
+
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
+  bool async = false;
   DBuf() {}
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
   ~DBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (async) cudaFreeAsync(p, st);
+      else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
-  void alloc(size_t count) {
+  void alloc(size_t count, cudaStream_t stream = nullptr) {
     release();
     n = count;
     if (count == 0) count = 1;
-    PSFM_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (stream) {
+      keep_pool_memory();
+      PSFM_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+      st = stream;
+      async = true;
+    } else {
+      PSFM_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+      async = false;
+    }
   }
   void upload(const T* h, size_t count, cudaStream_t s) {
     if (count) PSFM_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
