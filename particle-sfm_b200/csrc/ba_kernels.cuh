@@ -1,4 +1,5 @@
-// ba_kernels.cuh — sm_100a kernels of HP2 (global bundle adjustment).
+// ba_kernels.cuh — sm_100a tile kernels of HP2 (global bundle adjustment), FACTORED-JACOBIAN
+// formulation.
 //
 // Replaces what ceres::Solve does inside BundleAdjuster::Solve
 // (reference sfm/gmapper/src/optim/bundle_adjustment.cc:306): per-observation
@@ -7,13 +8,25 @@
 // (CreateLossFunction :54-69), per-point 3x3 Schur elimination and the implicit
 // reduced-camera-system product used by PCG.
 //
-// Data layout: observations sorted by point and packed into TILES of
-// <= TILE observations that never split a point; one CTA per tile, one thread per
-// observation.  Per-point sums are reduced inside the tile through shared memory (no
-// atomics, fixed order); per-image sums are reduced per (image-segment, component)
-// inside the tile with a host-precomputed in-tile image ordering, then one fp64 RED per
-// segment goes to the global accumulator.  Jacobians are stored SoA by component
-// ([k][M]) so that every global access of a warp is a contiguous 256-byte run.
+// Factored Jacobian.  For observation i of point p in image m the
+// loss-corrected Jacobian blocks of the reprojection residual are
+//     J_point = D_i R_m      J_trans = D_i      J_rot = D_i N(w_i)      J_focal = sq_i (u_i, v_i)'
+// with D_i = sqrt(rho') d r/d p = [[a00, 0, a02], [0, a00, a12]]   (3 distinct numbers),
+//      w_i = R_m X_p,  N(w) = -2 [w]x  (Ceres QuaternionParameterization: q+ = exp(d) (x) q),
+//      sq_i (u_i, v_i) = -(a02, a12) z_i / f,   z_i = w_i[2] + t_m[2].
+// Only (a00, a02, a12) and the corrected residual are STORED per observation (40 B instead
+// of the 176 B of an explicit 2x(6+3+1) Jacobian row pair); R_m, t_m and X_p are staged in
+// shared memory once per tile and every product with J or J' goes through the 3-vectors
+// D'v / D y.  Ceres' Jacobi column scaling never touches these kernels: all per-image and
+// per-point sums are accumulated UNSCALED and the diagonal scaling s is applied by the
+// O(#images)/O(#points) kernels of ba_small_kernels.cuh (J diag(s) is the scaled Jacobian,
+// so S_scaled = diag(s) S_unscaled diag(s) etc. — algebraically identical).
+//
+// Tiling: observations sorted by (point, image), packed into tiles of <= TILE observations
+// that never split a point; one CTA per tile, one thread per observation.  Per-point sums are
+// reduced inside the tile through shared memory in a fixed order (no atomics); per-image
+// sums are reduced per (image segment, component) inside the tile, then one fp64 RED per
+// segment goes to a replicated global accumulator (replica = tile mod NREP).
 #pragma once
 #include "psfm_common.cuh"
 
@@ -27,14 +40,15 @@ constexpr int NVI = 9;    // intrinsics accumulator stride per camera
 // accumulator is therefore replicated NREP times (replica = tile index mod NREP) and the
 // replicas are folded by k_fold_replicas before use.
 constexpr int NREP = 32;
-constexpr double kHuge = 1.7976931348623157e308;
 
 struct TileCtx {
   const int* tile_start;   // [T+1] first observation of each tile
   const int* tile_pt;      // [T+1] first (internal) point of each tile
   const int* pt_ptr;       // [P+1] observation range of each point
-  const int* obs_img;      // [M]
-  const int* obs_pt;       // [M] internal point id
+  const int* obs_img;      // [M]  (k_cost only)
+  const int* obs_pt;       // [M]  (k_cost only)
+  const unsigned short* obs_lseg;  // [M] index of the observation's image in the tile's segment list
+  const unsigned short* obs_lpt;   // [M] index of the observation's point inside the tile
   const double2* obs_xy;   // [M]
   const unsigned short* tile_perm;  // [M] e-th observation of the tile in image order
   const int* cseg_ptr;     // [T+1] image segments of each tile
@@ -42,13 +56,12 @@ struct TileCtx {
   const unsigned short* cseg_off;  // [nseg] start of the segment in the tile's image order
   const int* img_cam;      // [F]
   int F, P, M, C, T;
+  int cap_ns, cap_np;      // max segments / points of any tile (shared-memory sizing)
 };
 
-struct Jac {        // SoA by component, index k*M + i
+struct Lin {        // stored linearisation, SoA by component, index k*M + i
   double* r;        // [2][M] loss-corrected residuals
-  double* jc;       // [12][M] (ROT) or [6][M]: row0 cols.., row1 cols.. of the pose block
-  double* jp;       // [6][M]
-  double* jk;       // [4][M] focal column (2) then sq*s_cx, sq*s_cy (principal point)
+  double* a;        // [3][M] a00, a02, a12
 };
 
 struct LossP {
@@ -78,71 +91,104 @@ __device__ __forceinline__ void loss_eval(const LossP l, const double s, double&
 
 // ------------------------------------------------------------------ tile plumbing
 
-template <int TILE, int NV>
+// Shared memory of a tile kernel (all SoA so that lanes of one point / one image broadcast):
+//   sv   [NV][TILE]      per-observation values being reduced
+//   sw   [4][cap_np]     per-point scratch
+//   sred [9*32]          block-reduction scratch
+//   simg [12][cap_ns]    per image segment: R (row-major 9), t (3)
+//   sx   [6][cap_ns]     per image segment: scaled input vector (rot 3 | t 3)
+//   spt  [NPT][cap_np]   per point: X (3) [, H~ (6) [, w^ (3)]]
+template <int TILE>
 struct TileSmem {
-  double* sv;            // [NV][TILE] per-observation values being reduced
-  double* sw;            // [4][TILE] per-point scratch
-  double* sred;          // [8*32] block-reduction scratch
-  int* pstart;           // [TILE+1] local observation offset of each point of the tile
-  int* coff;             // [TILE+1] image-segment offsets (image order)
-  int* cimg;             // [TILE]
-  unsigned short* perm;  // [TILE]
-  static constexpr size_t bytes() {
-    return sizeof(double) * (size_t)(NV * TILE + 4 * TILE + 256) + sizeof(int) * (size_t)(3 * TILE + 2) +
-           sizeof(unsigned short) * (size_t)TILE + 16;
+  double *sv, *sw, *sred, *simg, *sx, *spt;
+  int *pstart, *coff, *cimg;
+  unsigned short* perm;
+  int cap_ns, cap_np;
+  static size_t bytes(int nv, int npt, int cap_ns, int cap_np) {
+    return sizeof(double) * ((size_t)nv * TILE + 4 * (size_t)cap_np + 9 * 32 + 18 * (size_t)cap_ns + (size_t)npt * cap_np) +
+           sizeof(int) * ((size_t)cap_np + 2 * (size_t)cap_ns + 4) + sizeof(unsigned short) * (size_t)TILE + 32;
   }
-  __device__ __forceinline__ void carve(unsigned char* base) {
+  __device__ __forceinline__ void carve(unsigned char* base, int nv, int npt, int cns, int cnp) {
+    cap_ns = cns; cap_np = cnp;
     sv = reinterpret_cast<double*>(base);
-    sw = sv + NV * TILE;
-    sred = sw + 4 * TILE;
-    pstart = reinterpret_cast<int*>(sred + 256);
-    coff = pstart + TILE + 1;
-    cimg = coff + TILE + 1;
-    perm = reinterpret_cast<unsigned short*>(cimg + TILE);
+    sw = sv + (size_t)nv * TILE;
+    sred = sw + 4 * (size_t)cnp;
+    simg = sred + 9 * 32;
+    sx = simg + 12 * (size_t)cns;
+    spt = sx + 6 * (size_t)cns;
+    pstart = reinterpret_cast<int*>(spt + (size_t)npt * cnp);
+    coff = pstart + cnp + 1;
+    cimg = coff + cns + 1;
+    perm = reinterpret_cast<unsigned short*>(cimg + cns + 1);
   }
 };
 
 struct TileInfo {
-  int base, n, pt0, np, ns;
+  int base, n, pt0, np, ns, cs0;
 };
 
-// Tile header: five scalar loads.  The caller then issues ALL of its global loads
-// (observation data, Jacobian rows, per-point blocks) before tile_fill_smem(), so that a
-// CTA pays one global-memory latency for the whole batch instead of one per stage.
-__device__ __forceinline__ TileInfo tile_header(const TileCtx& tc, int& cs0) {
+// Tile header: scalar loads.  The caller then issues ALL of its global loads before the
+// barrier of tile_fill_smem(), so that a CTA pays one global-memory latency for the batch.
+__device__ __forceinline__ TileInfo tile_header(const TileCtx& tc) {
   TileInfo ti;
   const int tile = blockIdx.x;
   ti.base = __ldg(tc.tile_start + tile);
   ti.n = __ldg(tc.tile_start + tile + 1) - ti.base;
   ti.pt0 = __ldg(tc.tile_pt + tile);
   ti.np = __ldg(tc.tile_pt + tile + 1) - ti.pt0;
-  cs0 = __ldg(tc.cseg_ptr + tile);
-  ti.ns = __ldg(tc.cseg_ptr + tile + 1) - cs0;
+  ti.cs0 = __ldg(tc.cseg_ptr + tile);
+  ti.ns = __ldg(tc.cseg_ptr + tile + 1) - ti.cs0;
   return ti;
 }
 
-template <int TILE, int NV>
-__device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE, NV>& sm, const TileInfo& ti,
-                                               int cs0, bool need_cam) {
+// pose16 row of an image: R (row-major 9), t (3), pad(4).  xs: scaled camera-side vector in
+// slot layout [6F + 3C] (may be null).  X: [3P] points.  p6/p3: optional per-point SoA arrays
+// ([6][P], [3][P]) staged after X.  Ends with a barrier.
+template <int TILE>
+__device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE>& sm, const TileInfo& ti,
+                                               const double* __restrict__ pose16, const double* __restrict__ xs,
+                                               const double* __restrict__ X, const double* __restrict__ p6,
+                                               const double* __restrict__ p3, bool need_cam) {
   const int tid = threadIdx.x;
+  const int cns = sm.cap_ns, cnp = sm.cap_np;
   for (int j = tid; j <= ti.np; j += TILE) sm.pstart[j] = __ldg(tc.pt_ptr + ti.pt0 + j) - ti.base;
+  for (int j = tid; j < ti.ns; j += TILE) {
+    sm.cimg[j] = __ldg(tc.cseg_img + ti.cs0 + j);
+    if (need_cam) sm.coff[j] = __ldg(tc.cseg_off + ti.cs0 + j);
+  }
   if (need_cam) {
-    for (int j = tid; j < ti.ns; j += TILE) {
-      sm.coff[j] = __ldg(tc.cseg_off + cs0 + j);
-      sm.cimg[j] = __ldg(tc.cseg_img + cs0 + j);
-    }
     if (tid == 0) sm.coff[ti.ns] = ti.n;
     if (tid < ti.n) sm.perm[tid] = __ldg(tc.tile_perm + ti.base + tid);
   }
+  for (int j = tid; j < ti.ns * 12; j += TILE) {
+    const int s = j / 12, k = j - 12 * s;
+    const int img = __ldg(tc.cseg_img + ti.cs0 + s);
+    sm.simg[k * cns + s] = __ldg(pose16 + 16 * (size_t)img + k);
+  }
+  if (xs) {
+    for (int j = tid; j < ti.ns * 6; j += TILE) {
+      const int s = j / 6, k = j - 6 * s;
+      const int img = __ldg(tc.cseg_img + ti.cs0 + s);
+      sm.sx[k * cns + s] = __ldg(xs + 6 * (size_t)img + k);
+    }
+  }
+  for (int j = tid; j < ti.np * 3; j += TILE) {
+    const int l = j / 3, k = j - 3 * l;
+    sm.spt[k * cnp + l] = __ldg(X + 3 * (size_t)ti.pt0 + j);
+  }
+  if (p6) {
+    for (int j = tid; j < ti.np * 6; j += TILE) {
+      const int k = j / ti.np, l = j - k * ti.np;
+      sm.spt[(3 + k) * cnp + l] = __ldg(p6 + (size_t)k * tc.P + ti.pt0 + l);
+    }
+  }
+  if (p3) {
+    for (int j = tid; j < ti.np * 3; j += TILE) {
+      const int k = j / ti.np, l = j - k * ti.np;
+      sm.spt[(9 + k) * cnp + l] = __ldg(p3 + (size_t)k * tc.P + ti.pt0 + l);
+    }
+  }
   __syncthreads();
-}
-
-template <int TILE, int NV>
-__device__ __forceinline__ TileInfo tile_prologue(const TileCtx& tc, TileSmem<TILE, NV>& sm, bool need_cam) {
-  int cs0;
-  const TileInfo ti = tile_header(tc, cs0);
-  tile_fill_smem<TILE, NV>(tc, sm, ti, cs0, need_cam);
-  return ti;
 }
 
 // N block sums with one barrier pair; results valid in threads 0..N-1 (thread j holds
@@ -164,246 +210,235 @@ __device__ __forceinline__ double block_sum_multi(const double (&v)[N], double* 
   return out;
 }
 
-// ------------------------------------------------------------------ projection
-
-struct Proj {
-  double R[9];
-  double w[3];   // R X
-  double p[3];   // R X + t
-  double u, v, iz;
-  double f;
-};
-
-__device__ __forceinline__ void load_pose(const double* __restrict__ pose, int img, double (&q)[4], double (&t)[3]) {
-  const double2* pp = reinterpret_cast<const double2*>(pose + 8 * (size_t)img);
-  const double2 a = __ldg(pp), b = __ldg(pp + 1), c = __ldg(pp + 2), d = __ldg(pp + 3);
-  q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
-  t[0] = c.x; t[1] = c.y; t[2] = d.x;
+// per (point, component) sums of sv rows [0, nv) -> fn(k, local point, sum)
+template <int TILE, typename Fn>
+__device__ __forceinline__ void tile_reduce_points(const TileSmem<TILE>& sm, const TileInfo& ti, int nv, Fn fn) {
+  for (int pair = threadIdx.x; pair < nv * ti.np; pair += TILE) {
+    const int k = pair / ti.np, l = pair - k * ti.np;
+    const double* row = sm.sv + k * TILE;
+    double acc = 0.0;
+    for (int e = sm.pstart[l]; e < sm.pstart[l + 1]; ++e) acc += row[e];
+    fn(k, l, acc);
+  }
 }
 
-__device__ __forceinline__ void project(const double (&q)[4], const double (&t)[3], const double* X, Proj& pr) {
-  const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-  pr.R[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3);
-  pr.R[1] = 2.0 * (q1 * q2 - q0 * q3);
-  pr.R[2] = 2.0 * (q1 * q3 + q0 * q2);
-  pr.R[3] = 2.0 * (q1 * q2 + q0 * q3);
-  pr.R[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3);
-  pr.R[5] = 2.0 * (q2 * q3 - q0 * q1);
-  pr.R[6] = 2.0 * (q1 * q3 - q0 * q2);
-  pr.R[7] = 2.0 * (q2 * q3 + q0 * q1);
-  pr.R[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    pr.w[a] = pr.R[3 * a] * X[0] + pr.R[3 * a + 1] * X[1] + pr.R[3 * a + 2] * X[2];
-    pr.p[a] = pr.w[a] + t[a];
+// per (image segment, component) sums of sv rows -> fn(k, image, sum)
+template <int TILE, typename Fn>
+__device__ __forceinline__ void tile_reduce_images(const TileSmem<TILE>& sm, const TileInfo& ti, int nv, Fn fn) {
+  for (int pair = threadIdx.x; pair < nv * ti.ns; pair += TILE) {
+    const int k = pair / ti.ns, s = pair - k * ti.ns;
+    const double* row = sm.sv + k * TILE;
+    double acc = 0.0;
+    for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
+    fn(k, sm.cimg[s], acc);
   }
-  pr.iz = 1.0 / pr.p[2];
-  pr.u = pr.p[0] * pr.iz;
-  pr.v = pr.p[1] * pr.iz;
+}
+
+// ------------------------------------------------------------------ per-observation geometry
+
+struct ObsGeom {
+  double R[9];
+  double w[3];      // R X
+  double tz;
+};
+
+template <int TILE>
+__device__ __forceinline__ void load_geom(const TileSmem<TILE>& sm, int ls, int lp, ObsGeom& g) {
+  const int cns = sm.cap_ns, cnp = sm.cap_np;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.R[k] = sm.simg[k * cns + ls];
+  g.tz = sm.simg[11 * cns + ls];
+  const double X0 = sm.spt[lp], X1 = sm.spt[cnp + lp], X2 = sm.spt[2 * cnp + lp];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g.w[a] = g.R[3 * a] * X0 + g.R[3 * a + 1] * X1 + g.R[3 * a + 2] * X2;
+}
+
+// u = J_cam x~  (unscaled J, scaled input): y3 = x~_t + 2 x~_r x w ; u = D y3 (+ focal / pp)
+template <int TILE, bool ROT>
+__device__ __forceinline__ void apply_Jc(const TileSmem<TILE>& sm, int ls, const ObsGeom& g, double a00, double a02,
+                                         double a12, int intr, const double* xk, double inv_f, double& u0, double& u1,
+                                         double& jf0, double& jf1, double& sq) {
+  const int cns = sm.cap_ns;
+  double y0 = sm.sx[3 * cns + ls], y1 = sm.sx[4 * cns + ls], y2 = sm.sx[5 * cns + ls];
+  if (ROT) {
+    const double r0 = sm.sx[ls], r1 = sm.sx[cns + ls], r2 = sm.sx[2 * cns + ls];
+    y0 += 2.0 * (r1 * g.w[2] - r2 * g.w[1]);
+    y1 += 2.0 * (r2 * g.w[0] - r0 * g.w[2]);
+    y2 += 2.0 * (r0 * g.w[1] - r1 * g.w[0]);
+  }
+  u0 = a00 * y0 + a02 * y2;
+  u1 = a00 * y1 + a12 * y2;
+  jf0 = jf1 = sq = 0.0;
+  if (intr >= 1) {
+    const double zf = (g.w[2] + g.tz) * inv_f;
+    jf0 = -a02 * zf;          // sq * u
+    jf1 = -a12 * zf;          // sq * v
+    u0 += jf0 * xk[0];
+    u1 += jf1 * xk[0];
+    if (intr == 3) {
+      sq = a00 * zf;
+      u0 += sq * xk[1];
+      u1 += sq * xk[2];
+    }
+  }
 }
 
 // ------------------------------------------------------------------ K1: Jacobian sweep
 
 struct LinArgs {
-  const double* pose;     // [F*8] q(4) t(3) pad
+  const double* pose16;   // [F*16] R(9) t(3)
   const double* X;        // [P*3]
   const double* K;        // [C*3]
-  const double* scale_c;  // [6F+3C] jacobi scaling, 0 on inactive slots
-  const double* scale_p;  // [3P]
   LossP loss;
   int intr;               // 0: intrinsics constant, 1: focal only, 3: focal + principal point
-  Jac J;
-  double* hpp;            // [6][P]  E'E (upper: 00 01 02 11 12 22)
+  Lin L;
+  double* hpp;            // [6][P]  E'E unscaled (upper: 00 01 02 11 12 22)
   double* gp;             // [3][P]  E'r
   double* wk;             // [9][P]  (G'E) rows: focal (3) | cx (3) | cy (3)
-  double* acc_cam;        // [NREP][F][NVL] rot F'F (6) | t F'F (6) | g (6)
-  size_t rep_stride;      // doubles between replicas
+  double* acc_cam;        // [NREP][F][NVL] rot F'F (6) | t F'F (6) | g rot (3) | g t (3)   (unscaled)
+  size_t rep_stride;
   double* acc_intr;       // [C][NVI] G'G (6: ff fx fy xx xy yy) | g_k (3)
   double* acc_cost;       // [1]
 };
 
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const TileCtx tc, const LinArgs a) {
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize(const TileCtx tc, const LinArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE, 18> sm;
-  sm.carve(smem_raw);
-  int cs0;
-  const TileInfo ti = tile_header(tc, cs0);
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 18, 3, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
-  const int M = tc.M;
+  const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
-  int img = 0, pt = 0;
+  int ls = 0, lp = 0;
   double2 xy = make_double2(0.0, 0.0);
   if (act) {
-    img = __ldg(tc.obs_img + i);
-    pt = __ldg(tc.obs_pt + i);
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
     xy = tc.obs_xy[i];
   }
-  tile_fill_smem<TILE, 18>(tc, sm, ti, cs0, true);
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, nullptr, nullptr, true);
 
-  double r0 = 0, r1 = 0, cost = 0;
-  double jr[2][3], jt[2][3], jp[2][3], jk[4];
+  double r0 = 0, r1 = 0, cost = 0, a00 = 0, a02 = 0, a12 = 0, jf0 = 0, jf1 = 0, sq = 0;
+  double jp0[3] = {0, 0, 0}, jp1[3] = {0, 0, 0};
+  ObsGeom g;
 #pragma unroll
-  for (int a_ = 0; a_ < 2; ++a_)
-#pragma unroll
-    for (int b_ = 0; b_ < 3; ++b_) { jr[a_][b_] = 0; jt[a_][b_] = 0; jp[a_][b_] = 0; }
-  jk[0] = jk[1] = jk[2] = jk[3] = 0;
-  int cam = 0;
+  for (int k = 0; k < 3; ++k) g.w[k] = 0.0;
   if (act) {
-    cam = tc.img_cam[img];
-    double q[4], t[3];
-    load_pose(a.pose, img, q, t);
-    const double X[3] = {a.X[3 * (size_t)pt], a.X[3 * (size_t)pt + 1], a.X[3 * (size_t)pt + 2]};
-    Proj pr;
-    project(q, t, X, pr);
-    const double f = a.K[3 * cam], cx = a.K[3 * cam + 1], cy = a.K[3 * cam + 2];
-    const double e0 = f * pr.u + cx - xy.x, e1 = f * pr.v + cy - xy.y;
+    load_geom<TILE>(sm, ls, lp, g);
+    const int cns = sm.cap_ns;
+    const double p0 = g.w[0] + sm.simg[9 * cns + ls], p1 = g.w[1] + sm.simg[10 * cns + ls], p2 = g.w[2] + g.tz;
+    const double iz = 1.0 / p2;
+    const double u = p0 * iz, v = p1 * iz;
+    const int cam = __ldg(tc.img_cam + sm.cimg[ls]);
+    const double f = __ldg(a.K + 3 * cam), cx = __ldg(a.K + 3 * cam + 1), cy = __ldg(a.K + 3 * cam + 2);
+    const double e0 = f * u + cx - xy.x, e1 = f * v + cy - xy.y;
     double rho0, rho1;
     loss_eval(a.loss, e0 * e0 + e1 * e1, rho0, rho1);
-    const double sq = sqrt(rho1);
+    sq = sqrt(rho1);
     cost = 0.5 * rho0;
     r0 = sq * e0;
     r1 = sq * e1;
-    const double a00 = sq * f * pr.iz, a02 = -a00 * pr.u, a12 = -a00 * pr.v;
-    const double* sp = a.scale_p + 3 * (size_t)pt;
-    const double* sc = a.scale_c + 6 * (size_t)img;
+    a00 = sq * f * iz;
+    a02 = -a00 * u;
+    a12 = -a00 * v;
+    a.L.r[i] = r0;
+    a.L.r[M + i] = r1;
+    a.L.a[i] = a00;
+    a.L.a[M + i] = a02;
+    a.L.a[2 * M + i] = a12;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double s = sp[k];
-      jp[0][k] = (a00 * pr.R[k] + a02 * pr.R[6 + k]) * s;
-      jp[1][k] = (a00 * pr.R[3 + k] + a12 * pr.R[6 + k]) * s;
+      jp0[k] = a00 * g.R[k] + a02 * g.R[6 + k];
+      jp1[k] = a00 * g.R[3 + k] + a12 * g.R[6 + k];
     }
-    jt[0][0] = a00 * sc[3]; jt[0][2] = a02 * sc[5];
-    jt[1][1] = a00 * sc[4]; jt[1][2] = a12 * sc[5];
-    if (ROT) {
-      // d r / d delta = (d r / d p) * (-2 [R X]x)  (QuaternionParameterization, Plus = exp(d) * q)
-      jr[0][0] = 2.0 * a02 * pr.w[1] * sc[0];
-      jr[0][1] = 2.0 * (a00 * pr.w[2] - a02 * pr.w[0]) * sc[1];
-      jr[0][2] = -2.0 * a00 * pr.w[1] * sc[2];
-      jr[1][0] = 2.0 * (a12 * pr.w[1] - a00 * pr.w[2]) * sc[0];
-      jr[1][1] = -2.0 * a12 * pr.w[0] * sc[1];
-      jr[1][2] = 2.0 * a00 * pr.w[0] * sc[2];
-    }
-    if (a.intr >= 1) {
-      const double* sk = a.scale_c + 6 * (size_t)tc.F + 3 * cam;
-      jk[0] = sq * pr.u * sk[0];
-      jk[1] = sq * pr.v * sk[0];
-      if (a.intr == 3) { jk[2] = sq * sk[1]; jk[3] = sq * sk[2]; }
-    }
-    // ---- store the linearisation (SoA, coalesced) ----
-    a.J.r[i] = r0;
-    a.J.r[(size_t)M + i] = r1;
-    if (ROT) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        a.J.jc[(size_t)k * M + i] = jr[0][k];
-        a.J.jc[(size_t)(3 + k) * M + i] = jt[0][k];
-        a.J.jc[(size_t)(6 + k) * M + i] = jr[1][k];
-        a.J.jc[(size_t)(9 + k) * M + i] = jt[1][k];
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        a.J.jc[(size_t)k * M + i] = jt[0][k];
-        a.J.jc[(size_t)(3 + k) * M + i] = jt[1][k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      a.J.jp[(size_t)k * M + i] = jp[0][k];
-      a.J.jp[(size_t)(3 + k) * M + i] = jp[1][k];
-    }
-    if (a.intr >= 1) {
-      a.J.jk[i] = jk[0];
-      a.J.jk[(size_t)M + i] = jk[1];
-      if (a.intr == 3) { a.J.jk[2 * (size_t)M + i] = jk[2]; a.J.jk[3 * (size_t)M + i] = jk[3]; }
-    }
+    jf0 = sq * u;
+    jf1 = sq * v;
   }
 
   // ---- point side: E'E (6), E'r (3), G'E (3 per free intrinsic) ----
   const int nvp = 9 + 3 * a.intr;
   {
     double* sv = sm.sv + tid;
-    sv[0 * TILE] = jp[0][0] * jp[0][0] + jp[1][0] * jp[1][0];
-    sv[1 * TILE] = jp[0][0] * jp[0][1] + jp[1][0] * jp[1][1];
-    sv[2 * TILE] = jp[0][0] * jp[0][2] + jp[1][0] * jp[1][2];
-    sv[3 * TILE] = jp[0][1] * jp[0][1] + jp[1][1] * jp[1][1];
-    sv[4 * TILE] = jp[0][1] * jp[0][2] + jp[1][1] * jp[1][2];
-    sv[5 * TILE] = jp[0][2] * jp[0][2] + jp[1][2] * jp[1][2];
+    sv[0 * TILE] = jp0[0] * jp0[0] + jp1[0] * jp1[0];
+    sv[1 * TILE] = jp0[0] * jp0[1] + jp1[0] * jp1[1];
+    sv[2 * TILE] = jp0[0] * jp0[2] + jp1[0] * jp1[2];
+    sv[3 * TILE] = jp0[1] * jp0[1] + jp1[1] * jp1[1];
+    sv[4 * TILE] = jp0[1] * jp0[2] + jp1[1] * jp1[2];
+    sv[5 * TILE] = jp0[2] * jp0[2] + jp1[2] * jp1[2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sv[(6 + k) * TILE] = jp[0][k] * r0 + jp[1][k] * r1;
+    for (int k = 0; k < 3; ++k) sv[(6 + k) * TILE] = jp0[k] * r0 + jp1[k] * r1;
     if (a.intr >= 1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) sv[(9 + k) * TILE] = jk[0] * jp[0][k] + jk[1] * jp[1][k];
+      for (int k = 0; k < 3; ++k) sv[(9 + k) * TILE] = jf0 * jp0[k] + jf1 * jp1[k];
       if (a.intr == 3) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          sv[(12 + k) * TILE] = jk[2] * jp[0][k];
-          sv[(15 + k) * TILE] = jk[3] * jp[1][k];
+          sv[(12 + k) * TILE] = sq * jp0[k];
+          sv[(15 + k) * TILE] = sq * jp1[k];
         }
       }
     }
   }
   __syncthreads();
-  for (int pair = tid; pair < nvp * ti.np; pair += TILE) {
-    const int k = pair / ti.np, lp = pair - k * ti.np;
-    double acc = 0.0;
-    const double* row = sm.sv + k * TILE;
-    for (int e = sm.pstart[lp]; e < sm.pstart[lp + 1]; ++e) acc += row[e];
-    const size_t gpt = (size_t)ti.pt0 + lp;
+  tile_reduce_points<TILE>(sm, ti, nvp, [&](int k, int l, double acc) {
+    const size_t gpt = (size_t)ti.pt0 + l;
     if (k < 6) a.hpp[(size_t)k * tc.P + gpt] = acc;
     else if (k < 9) a.gp[(size_t)(k - 6) * tc.P + gpt] = acc;
     else a.wk[(size_t)(k - 9) * tc.P + gpt] = acc;
-  }
+  });
   __syncthreads();
 
-  // ---- image side: diagonal 3x3 blocks of F'F (rot | t) and F'r ----
+  // ---- image side: diagonal 3x3 blocks of F'F (rot | t) and F'r, unscaled ----
   {
     double* sv = sm.sv + tid;
     if (ROT) {
-      sv[0 * TILE] = jr[0][0] * jr[0][0] + jr[1][0] * jr[1][0];
-      sv[1 * TILE] = jr[0][0] * jr[0][1] + jr[1][0] * jr[1][1];
-      sv[2 * TILE] = jr[0][0] * jr[0][2] + jr[1][0] * jr[1][2];
-      sv[3 * TILE] = jr[0][1] * jr[0][1] + jr[1][1] * jr[1][1];
-      sv[4 * TILE] = jr[0][1] * jr[0][2] + jr[1][1] * jr[1][2];
-      sv[5 * TILE] = jr[0][2] * jr[0][2] + jr[1][2] * jr[1][2];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) sv[(12 + k) * TILE] = jr[0][k] * r0 + jr[1][k] * r1;
+      const double jr00 = 2.0 * a02 * g.w[1], jr01 = 2.0 * (a00 * g.w[2] - a02 * g.w[0]), jr02 = -2.0 * a00 * g.w[1];
+      const double jr10 = 2.0 * (a12 * g.w[1] - a00 * g.w[2]), jr11 = -2.0 * a12 * g.w[0], jr12 = 2.0 * a00 * g.w[0];
+      sv[0 * TILE] = jr00 * jr00 + jr10 * jr10;
+      sv[1 * TILE] = jr00 * jr01 + jr10 * jr11;
+      sv[2 * TILE] = jr00 * jr02 + jr10 * jr12;
+      sv[3 * TILE] = jr01 * jr01 + jr11 * jr11;
+      sv[4 * TILE] = jr01 * jr02 + jr11 * jr12;
+      sv[5 * TILE] = jr02 * jr02 + jr12 * jr12;
+      sv[12 * TILE] = jr00 * r0 + jr10 * r1;
+      sv[13 * TILE] = jr01 * r0 + jr11 * r1;
+      sv[14 * TILE] = jr02 * r0 + jr12 * r1;
     }
-    sv[6 * TILE] = jt[0][0] * jt[0][0];
+    sv[6 * TILE] = a00 * a00;
     sv[7 * TILE] = 0.0;
-    sv[8 * TILE] = jt[0][0] * jt[0][2];
-    sv[9 * TILE] = jt[1][1] * jt[1][1];
-    sv[10 * TILE] = jt[1][1] * jt[1][2];
-    sv[11 * TILE] = jt[0][2] * jt[0][2] + jt[1][2] * jt[1][2];
-    sv[15 * TILE] = jt[0][0] * r0;
-    sv[16 * TILE] = jt[1][1] * r1;
-    sv[17 * TILE] = jt[0][2] * r0 + jt[1][2] * r1;
+    sv[8 * TILE] = a00 * a02;
+    sv[9 * TILE] = a00 * a00;
+    sv[10 * TILE] = a00 * a12;
+    sv[11 * TILE] = a02 * a02 + a12 * a12;
+    sv[15 * TILE] = a00 * r0;
+    sv[16 * TILE] = a00 * r1;
+    sv[17 * TILE] = a02 * r0 + a12 * r1;
   }
   __syncthreads();
   {
-    // components handled: ROT -> 0..17, else 6..11 and 15..17 (9 values)
+    // components handled: ROT -> 0..17, else 6..11 and 15..17 (9 values); 7 is structurally 0
+    double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
     const int nvc = ROT ? 18 : 9;
     for (int pair = tid; pair < nvc * ti.ns; pair += TILE) {
       int k = pair / ti.ns;
       const int s = pair - k * ti.ns;
       if (!ROT) k = (k < 6) ? k + 6 : k + 9;
-      if (k == 7) continue;  // structurally zero
+      if (k == 7) continue;
       const double* row = sm.sv + k * TILE;
       double acc = 0.0;
       for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-      atomicAdd(a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + (size_t)sm.cimg[s] * NVL + k, acc);
+      atomicAdd(dst + (size_t)sm.cimg[s] * NVL + k, acc);
     }
   }
-  // ---- cost and intrinsics (block sums) ----
+  // ---- cost and intrinsics (block sums; a single shared camera when intrinsics are free) ----
   {
     double v[3];
     v[0] = cost;
-    v[1] = jk[0] * jk[0] + jk[1] * jk[1];
-    v[2] = jk[0] * r0 + jk[1] * r1;
+    v[1] = jf0 * jf0 + jf1 * jf1;
+    v[2] = jf0 * r0 + jf1 * r1;
     const double s = block_sum_multi<3>(v, sm.sred);
-    // single shared camera when intrinsics are free (checked on the host); cost always
     if (tid == 0) atomicAdd(a.acc_cost, s);
     if (a.intr >= 1) {
       if (tid == 1) atomicAdd(a.acc_intr + 0, s);
@@ -411,13 +446,13 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const
     }
     if (a.intr == 3) {
       double u[7];
-      u[0] = jk[0] * jk[2];            // f-cx
-      u[1] = jk[1] * jk[3];            // f-cy
-      u[2] = jk[2] * jk[2];            // cx-cx
+      u[0] = jf0 * sq;                 // f-cx
+      u[1] = jf1 * sq;                 // f-cy
+      u[2] = act ? sq * sq : 0.0;      // cx-cx
       u[3] = 0.0;                      // cx-cy
-      u[4] = jk[3] * jk[3];            // cy-cy
-      u[5] = jk[2] * r0;               // g cx
-      u[6] = jk[3] * r1;               // g cy
+      u[4] = act ? sq * sq : 0.0;      // cy-cy
+      u[5] = sq * r0;                  // g cx
+      u[6] = sq * r1;                  // g cy
       const double s2 = block_sum_multi<7>(u, sm.sred);
       if (tid < 5) atomicAdd(a.acc_intr + 1 + tid, s2);
       else if (tid < 7) atomicAdd(a.acc_intr + 7 + (tid - 5), s2);
@@ -428,18 +463,18 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_linearize(const
 // ------------------------------------------------------------------ K2: point blocks
 
 struct PtsArgs {
-  const double* hpp;   // [6][P]
-  const double* gp;    // [3][P]
-  const double* wk;    // [9][P]
+  const double* hpp;   // [6][P] unscaled E'E
+  const double* gp;    // [3][P] unscaled E'r
+  const double* wk;    // [9][P] unscaled G'E
   const double* scale_p;  // [3P]
   double radius, min_diag, max_diag;
   int intr;
   int P;
-  double* hinv;        // [6][P] (E'E + D^2)^-1 upper
-  double* w;           // [3][P] hinv * E'r
-  double* acc_intr;    // [NVI] -(G'E) hinv (E'G) (6) | -(G'E) hinv E'r (3)
+  double* ht;          // [6][P] H~ = diag(s_p) (s_p E'E s_p + D^2)^-1 diag(s_p)
+  double* wt;          // [3][P] w^ = H~ E'r
+  double* acc_intr;    // [NVI] -(G'E) H~ (E'G) (6) | -(G'E) w^ (3)   (unscaled in the intrinsics)
   double* acc_fail;    // [1] > 0 when a block is not positive definite
-  double* gmax;        // [1] max |unscaled gradient| over point parameters (atomic max)
+  double* gmax;        // [1] max |gradient| over point parameters (atomic max)
 };
 
 __global__ void __launch_bounds__(256) k_point_blocks(const PtsArgs a) {
@@ -451,10 +486,11 @@ __global__ void __launch_bounds__(256) k_point_blocks(const PtsArgs a) {
   for (int k = 0; k < 9; ++k) ci[k] = 0.0;
   if (p < a.P) {
     const size_t P = a.P;
-    double h00 = a.hpp[p], h01 = a.hpp[P + p], h02 = a.hpp[2 * P + p], h11 = a.hpp[3 * P + p],
-           h12 = a.hpp[4 * P + p], h22 = a.hpp[5 * P + p];
+    const double s0 = a.scale_p[3 * (size_t)p], s1 = a.scale_p[3 * (size_t)p + 1], s2 = a.scale_p[3 * (size_t)p + 2];
+    double h00 = a.hpp[p] * s0 * s0, h01 = a.hpp[P + p] * s0 * s1, h02 = a.hpp[2 * P + p] * s0 * s2,
+           h11 = a.hpp[3 * P + p] * s1 * s1, h12 = a.hpp[4 * P + p] * s1 * s2, h22 = a.hpp[5 * P + p] * s2 * s2;
     const double g0 = a.gp[p], g1 = a.gp[P + p], g2 = a.gp[2 * P + p];
-    // LevenbergMarquardtStrategy: D^2 = clamp(diag(J'J)) / radius
+    // LevenbergMarquardtStrategy: D^2 = clamp(diag(J'J)) / radius  (scaled Jacobian)
     h00 += fmin(fmax(h00, a.min_diag), a.max_diag) / a.radius;
     h11 += fmin(fmax(h11, a.min_diag), a.max_diag) / a.radius;
     h22 += fmin(fmax(h22, a.min_diag), a.max_diag) / a.radius;
@@ -476,14 +512,15 @@ __global__ void __launch_bounds__(256) k_point_blocks(const PtsArgs a) {
     double v00 = i00 * i00 + i10 * i10 + i20 * i20, v01 = i10 * i11 + i20 * i21, v02 = i20 * i22,
            v11 = i11 * i11 + i21 * i21, v12 = i21 * i22, v22 = i22 * i22;
     if (bad) { fail = 1.0; v00 = v11 = v22 = 1.0; v01 = v02 = v12 = 0.0; }
-    a.hinv[p] = v00; a.hinv[P + p] = v01; a.hinv[2 * P + p] = v02;
-    a.hinv[3 * P + p] = v11; a.hinv[4 * P + p] = v12; a.hinv[5 * P + p] = v22;
+    // H~ = diag(s) Hinv diag(s)
+    v00 *= s0 * s0; v01 *= s0 * s1; v02 *= s0 * s2; v11 *= s1 * s1; v12 *= s1 * s2; v22 *= s2 * s2;
+    a.ht[p] = v00; a.ht[P + p] = v01; a.ht[2 * P + p] = v02;
+    a.ht[3 * P + p] = v11; a.ht[4 * P + p] = v12; a.ht[5 * P + p] = v22;
     const double w0 = v00 * g0 + v01 * g1 + v02 * g2;
     const double w1 = v01 * g0 + v11 * g1 + v12 * g2;
     const double w2 = v02 * g0 + v12 * g1 + v22 * g2;
-    a.w[p] = w0; a.w[P + p] = w1; a.w[2 * P + p] = w2;
-    const double* sp = a.scale_p + 3 * (size_t)p;
-    gm = fmax(fmax(fabs(g0 / sp[0]), fabs(g1 / sp[1])), fabs(g2 / sp[2]));
+    a.wt[p] = w0; a.wt[P + p] = w1; a.wt[2 * P + p] = w2;
+    gm = fmax(fmax(fabs(g0), fabs(g1)), fabs(g2));
     if (a.intr >= 1) {
       double W[3][3], WH[3][3];
       for (int j = 0; j < 3; ++j)
@@ -512,49 +549,59 @@ __global__ void __launch_bounds__(256) k_point_blocks(const PtsArgs a) {
 // ------------------------------------------------------------------ K3: Schur-Jacobi / rhs corrections
 
 struct PrepArgs {
-  Jac J;
-  const double* hinv;   // [6][P]
-  const double* w;      // [3][P]
-  double* acc_cam;      // [NREP][F][NVL]: -(W hinv W') rot (6) | t (6) | -(W w) (6)
+  Lin L;
+  const double* pose16;
+  const double* X;
+  const double* ht;     // [6][P]
+  const double* wt;     // [3][P]
+  double* acc_cam;      // [NREP][F][NVL]: -(W H~ W') rot (6) | t (6) | -(W w^) rot (3) | t (3)   (unscaled)
   size_t rep_stride;
 };
 
 template <int TILE, bool ROT>
 __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(const TileCtx tc, const PrepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE, 18> sm;
-  sm.carve(smem_raw);
-  int cs0;
-  const TileInfo ti = tile_header(tc, cs0);
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 18, 12, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
-  const size_t M = tc.M, P = tc.P;
+  const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
-  constexpr int NCP = ROT ? 6 : 3;
-  double jp[2][3], hv[6], w[3], jcr0[NCP], jcr1[NCP];
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0;
   if (act) {
-    const int pt = __ldg(tc.obs_pt + i);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
-#pragma unroll
-    for (int k = 0; k < NCP; ++k) { jcr0[k] = a.J.jc[(size_t)k * M + i]; jcr1[k] = a.J.jc[(size_t)(NCP + k) * M + i]; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hv[k] = a.hinv[k * P + pt];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) w[k] = a.w[k * P + pt];
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
   }
-  tile_fill_smem<TILE, 18>(tc, sm, ti, cs0, true);
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wt, true);
   double* sv = sm.sv + tid;
   if (act) {
+    ObsGeom g;
+    load_geom<TILE>(sm, ls, lp, g);
+    const int cnp = sm.cap_np;
+    double hv[6], w[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = sm.spt[(9 + k) * cnp + lp];
+    double jp[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      jp[0][k] = a00 * g.R[k] + a02 * g.R[6 + k];
+      jp[1][k] = a00 * g.R[3 + k] + a12 * g.R[6 + k];
+    }
     // block b: 0 = rot (ROT only), 1 = translation
 #pragma unroll
     for (int b = (ROT ? 0 : 1); b < 2; ++b) {
       double jc0[3], jc1[3];
-      const int off = ROT ? 3 * b : 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        jc0[k] = jcr0[off + k];
-        jc1[k] = jcr1[off + k];
+      if (b == 0) {
+        jc0[0] = 2.0 * a02 * g.w[1]; jc0[1] = 2.0 * (a00 * g.w[2] - a02 * g.w[0]); jc0[2] = -2.0 * a00 * g.w[1];
+        jc1[0] = 2.0 * (a12 * g.w[1] - a00 * g.w[2]); jc1[1] = -2.0 * a12 * g.w[0]; jc1[2] = 2.0 * a00 * g.w[0];
+      } else {
+        jc0[0] = a00; jc0[1] = 0.0; jc0[2] = a02;
+        jc1[0] = 0.0; jc1[1] = a00; jc1[2] = a12;
       }
       double W[3][3], WH[3][3];
 #pragma unroll
@@ -577,6 +624,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
     }
   }
   __syncthreads();
+  double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
   const int nvc = ROT ? 18 : 9;
   for (int pair = tid; pair < nvc * ti.ns; pair += TILE) {
     int k = pair / ti.ns;
@@ -585,117 +633,117 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
     const double* row = sm.sv + k * TILE;
     double acc = 0.0;
     for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-    atomicAdd(a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + (size_t)sm.cimg[s] * NVL + k, acc);
+    atomicAdd(dst + (size_t)sm.cimg[s] * NVL + k, acc);
   }
 }
 
 // ------------------------------------------------------------------ K4: implicit S * p
 
 struct SpArgs {
-  Jac J;
-  const double* hinv;   // [6][P]
-  const double* x;      // [6F + 3C] input vector (slot layout)
-  double* y;            // [NREP][6F + 3C] += F'(I - E hinv E') F x  (D^2 x is added by the PCG kernel)
+  Lin L;
+  const double* pose16;
+  const double* X;
+  const double* ht;     // [6][P]
+  const double* xs;     // [6F + 3C] scaled input vector s o x (slot layout)
+  double* y;            // [NREP][6F + 3C] += F'(I - E H~ E') F xs   (unscaled; folded and scaled later)
   size_t rep_stride;
   const int* flag;      // PCG state: != 0 -> nothing to do
+  const double* K;      // [3C]
   int intr;
 };
 
 #ifndef PSFM_SP_MINB
-#define PSFM_SP_MINB 3
+#define PSFM_SP_MINB 4
 #endif
 template <int TILE, bool ROT>
 __global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schur_product(const TileCtx tc, const SpArgs a) {
   if (*a.flag != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE, 6> sm;
-  sm.carve(smem_raw);
-  int cs0;
-  const TileInfo ti = tile_header(tc, cs0);
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 6, 9, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
-  const size_t M = tc.M, P = tc.P;
+  const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
-  constexpr int NC = ROT ? 6 : 3;
-  double jc0[NC], jc1[NC], jp[2][3], jk[4] = {0, 0, 0, 0};
-  double hp[6] = {0, 0, 0, 0, 0, 0};
-  double u0 = 0, u1 = 0;
-  int img = 0, lp = 0;
-  const double* xk = a.x + 6 * (size_t)tc.F;   // single shared camera when intr > 0
-#pragma unroll
-  for (int k = 0; k < NC; ++k) { jc0[k] = 0; jc1[k] = 0; }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { jp[0][k] = 0; jp[1][k] = 0; }
-  // ---- every global load of the tile is issued here, before the first barrier ----
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0;
   if (act) {
-    img = __ldg(tc.obs_img + i);
-    lp = __ldg(tc.obs_pt + i) - ti.pt0;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) { jc0[k] = a.J.jc[(size_t)k * M + i]; jc1[k] = a.J.jc[(size_t)(NC + k) * M + i]; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
-    if (a.intr >= 1) {
-      jk[0] = a.J.jk[i]; jk[1] = a.J.jk[M + i];
-      if (a.intr == 3) { jk[2] = a.J.jk[2 * M + i]; jk[3] = a.J.jk[3 * M + i]; }
-    }
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
   }
-  if (tid < ti.np) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hp[k] = a.hinv[k * P + (size_t)ti.pt0 + tid];
+  double xk[3] = {0, 0, 0};
+  double inv_f = 0.0;
+  if (a.intr >= 1) {
+    xk[0] = __ldg(a.xs + 6 * (size_t)tc.F); xk[1] = __ldg(a.xs + 6 * (size_t)tc.F + 1); xk[2] = __ldg(a.xs + 6 * (size_t)tc.F + 2);
+    inv_f = 1.0 / __ldg(a.K);
   }
-  tile_fill_smem<TILE, 6>(tc, sm, ti, cs0, true);
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, a.xs, a.X, a.ht, nullptr, true);
+  ObsGeom g;
+  double u0 = 0, u1 = 0, jf0 = 0, jf1 = 0, sq = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.R[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g.w[k] = 0.0;
   if (act) {
-    const double* xi = a.x + 6 * (size_t)img + (ROT ? 0 : 3);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) { const double xv = __ldg(xi + k); u0 += jc0[k] * xv; u1 += jc1[k] * xv; }
-    if (a.intr >= 1) {
-      const double xf = __ldg(xk);
-      u0 += jk[0] * xf; u1 += jk[1] * xf;
-      if (a.intr == 3) {
-        u0 += jk[2] * __ldg(xk + 1);
-        u1 += jk[3] * __ldg(xk + 2);
-      }
-    }
+    load_geom<TILE>(sm, ls, lp, g);
+    apply_Jc<TILE, ROT>(sm, ls, g, a00, a02, a12, a.intr, xk, inv_f, u0, u1, jf0, jf1, sq);
   }
   double* sv = sm.sv + tid;
+  {
+    // E'u = R'(D'u)
+    const double d0 = a00 * u0, d1 = a00 * u1, d2 = a02 * u0 + a12 * u1;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) sv[k * TILE] = jp[0][k] * u0 + jp[1][k] * u1;
-  __syncthreads();
-  // per point: t = E'u ; w = hinv t
-  for (int pair = tid; pair < 3 * ti.np; pair += TILE) {
-    const int k = pair / ti.np, l = pair - k * ti.np;
-    const double* row = sm.sv + k * TILE;
-    double acc = 0.0;
-    for (int e = sm.pstart[l]; e < sm.pstart[l + 1]; ++e) acc += row[e];
-    sm.sw[k * TILE + l] = acc;
+    for (int k = 0; k < 3; ++k) sv[k * TILE] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
   }
+  __syncthreads();
+  const int cnp = sm.cap_np;
+  tile_reduce_points<TILE>(sm, ti, 3, [&](int k, int l, double acc) { sm.sw[k * cnp + l] = acc; });
   __syncthreads();
   if (tid < ti.np) {
-    const double t0 = sm.sw[tid], t1 = sm.sw[TILE + tid], t2 = sm.sw[2 * TILE + tid];
-    sm.sw[tid] = hp[0] * t0 + hp[1] * t1 + hp[2] * t2;
-    sm.sw[TILE + tid] = hp[1] * t0 + hp[3] * t1 + hp[4] * t2;
-    sm.sw[2 * TILE + tid] = hp[2] * t0 + hp[4] * t1 + hp[5] * t2;
+    const double t0 = sm.sw[tid], t1 = sm.sw[cnp + tid], t2 = sm.sw[2 * cnp + tid];
+    const double h0 = sm.spt[3 * cnp + tid], h1 = sm.spt[4 * cnp + tid], h2 = sm.spt[5 * cnp + tid],
+                 h3 = sm.spt[6 * cnp + tid], h4 = sm.spt[7 * cnp + tid], h5 = sm.spt[8 * cnp + tid];
+    sm.sw[tid] = h0 * t0 + h1 * t1 + h2 * t2;
+    sm.sw[cnp + tid] = h1 * t0 + h3 * t1 + h4 * t2;
+    sm.sw[2 * cnp + tid] = h2 * t0 + h4 * t1 + h5 * t2;
   }
   __syncthreads();
-  const double w0 = sm.sw[lp], w1 = sm.sw[TILE + lp], w2 = sm.sw[2 * TILE + lp];
-  const double v0 = u0 - (jp[0][0] * w0 + jp[0][1] * w1 + jp[0][2] * w2);
-  const double v1 = u1 - (jp[1][0] * w0 + jp[1][1] * w1 + jp[1][2] * w2);
-  __syncthreads();   // sv is rewritten below; sw reads are done
-#pragma unroll
-  for (int k = 0; k < NC; ++k) sv[k * TILE] = act ? (jc0[k] * v0 + jc1[k] * v1) : 0.0;
+  double v0 = 0, v1 = 0;
+  {
+    const double z0 = sm.sw[lp], z1 = sm.sw[cnp + lp], z2 = sm.sw[2 * cnp + lp];
+    // E z = D (R z)
+    const double y0 = g.R[0] * z0 + g.R[1] * z1 + g.R[2] * z2;
+    const double y1 = g.R[3] * z0 + g.R[4] * z1 + g.R[5] * z2;
+    const double y2 = g.R[6] * z0 + g.R[7] * z1 + g.R[8] * z2;
+    v0 = u0 - (a00 * y0 + a02 * y2);
+    v1 = u1 - (a00 * y1 + a12 * y2);
+  }
+  __syncthreads();   // sv is rewritten below
+  {
+    // F'v: e = D'v ; rot = 2 w x e ; t = e
+    const double e0 = a00 * v0, e1 = a00 * v1, e2 = a02 * v0 + a12 * v1;
+    if (ROT) {
+      sv[0 * TILE] = 2.0 * (g.w[1] * e2 - g.w[2] * e1);
+      sv[1 * TILE] = 2.0 * (g.w[2] * e0 - g.w[0] * e2);
+      sv[2 * TILE] = 2.0 * (g.w[0] * e1 - g.w[1] * e0);
+      sv[3 * TILE] = e0; sv[4 * TILE] = e1; sv[5 * TILE] = e2;
+    } else {
+      sv[0 * TILE] = e0; sv[1 * TILE] = e1; sv[2 * TILE] = e2;
+    }
+  }
   __syncthreads();
-  for (int pair = tid; pair < NC * ti.ns; pair += TILE) {
-    const int k = pair / ti.ns, s = pair - k * ti.ns;
-    const double* row = sm.sv + k * TILE;
-    double acc = 0.0;
-    for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
-    atomicAdd(a.y + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + 6 * (size_t)sm.cimg[s] + (ROT ? 0 : 3) + k, acc);
+  {
+    constexpr int NC = ROT ? 6 : 3;
+    double* dst = a.y + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + (ROT ? 0 : 3);
+    tile_reduce_images<TILE>(sm, ti, NC, [&](int k, int img, double acc) { atomicAdd(dst + 6 * (size_t)img + k, acc); });
   }
   if (a.intr >= 1) {
     double v[3];
-    v[0] = act ? jk[0] * v0 + jk[1] * v1 : 0.0;
-    v[1] = act ? jk[2] * v0 : 0.0;
-    v[2] = act ? jk[3] * v1 : 0.0;
+    v[0] = jf0 * v0 + jf1 * v1;
+    v[1] = sq * v0;
+    v[2] = sq * v1;
     const double s = block_sum_multi<3>(v, sm.sred);
     if (tid < a.intr) atomicAdd(a.y + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride + 6 * (size_t)tc.F + tid, s);
   }
@@ -704,109 +752,91 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schu
 // ------------------------------------------------------------------ K5: back-substitution + model cost + candidate points
 
 struct BackArgs {
-  Jac J;
-  const double* hinv;   // [6][P]
-  const double* w;      // [3][P] hinv * E'r
-  const double* yc;     // [6F + 3C] reduced-system solution (step_c = -yc)
-  const double* scale_p;
+  Lin L;
+  const double* pose16;
   const double* X;      // [3P] current points
+  const double* ht;     // [6][P]
+  const double* wt;     // [3][P] H~ E'r
+  const double* xs;     // [6F + 3C] s o y_c  (y_c = reduced-system solution; step_c = -y_c)
+  const double* K;
   double* Xc;           // [3P] candidate points
   double* acc;          // [0] sum m(r + m/2)   [1] |dX|^2   [2] |Xc|^2
   int intr;
 };
 
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE, 6> sm;
-  sm.carve(smem_raw);
-  int cs0;
-  const TileInfo ti = tile_header(tc, cs0);
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 3, 12, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
-  const size_t M = tc.M, P = tc.P;
+  const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
-  constexpr int NC = ROT ? 6 : 3;
-  double jc0[NC], jc1[NC], jp[2][3], jk[4] = {0, 0, 0, 0};
-  double u0 = 0, u1 = 0, r0 = 0, r1 = 0;
-  int img = 0, lp = 0;
-#pragma unroll
-  for (int k = 0; k < NC; ++k) { jc0[k] = 0; jc1[k] = 0; }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { jp[0][k] = 0; jp[1][k] = 0; }
-  // ---- all global loads up front ----
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0, r0 = 0, r1 = 0;
   if (act) {
-    img = __ldg(tc.obs_img + i);
-    lp = __ldg(tc.obs_pt + i) - ti.pt0;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) { jc0[k] = a.J.jc[(size_t)k * M + i]; jc1[k] = a.J.jc[(size_t)(NC + k) * M + i]; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { jp[0][k] = a.J.jp[k * M + i]; jp[1][k] = a.J.jp[(3 + k) * M + i]; }
-    if (a.intr >= 1) {
-      jk[0] = a.J.jk[i]; jk[1] = a.J.jk[M + i];
-      if (a.intr == 3) { jk[2] = a.J.jk[2 * M + i]; jk[3] = a.J.jk[3 * M + i]; }
-    }
-    r0 = a.J.r[i]; r1 = a.J.r[M + i];
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
+    r0 = a.L.r[i]; r1 = a.L.r[M + i];
   }
-  double hp[6] = {0, 0, 0, 0, 0, 0}, wp[3] = {0, 0, 0}, spp[3] = {0, 0, 0}, Xp[3] = {0, 0, 0};
-  if (tid < ti.np) {
-    const size_t g = (size_t)ti.pt0 + tid;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hp[k] = a.hinv[k * P + g];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { wp[k] = a.w[k * P + g]; spp[k] = a.scale_p[3 * g + k]; Xp[k] = a.X[3 * g + k]; }
+  double xk[3] = {0, 0, 0};
+  double inv_f = 0.0;
+  if (a.intr >= 1) {
+    xk[0] = __ldg(a.xs + 6 * (size_t)tc.F); xk[1] = __ldg(a.xs + 6 * (size_t)tc.F + 1); xk[2] = __ldg(a.xs + 6 * (size_t)tc.F + 2);
+    inv_f = 1.0 / __ldg(a.K);
   }
-  tile_fill_smem<TILE, 6>(tc, sm, ti, cs0, false);
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, a.xs, a.X, a.ht, a.wt, false);
+  ObsGeom g;
+  double u0 = 0, u1 = 0, jf0 = 0, jf1 = 0, sq = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.R[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g.w[k] = 0.0;
   if (act) {
-    const double* xi = a.yc + 6 * (size_t)img + (ROT ? 0 : 3);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const double xv = __ldg(xi + k);
-      u0 += jc0[k] * xv;
-      u1 += jc1[k] * xv;
-    }
-    if (a.intr >= 1) {
-      const double* xk = a.yc + 6 * (size_t)tc.F;
-      const double xf = __ldg(xk);
-      u0 += jk[0] * xf; u1 += jk[1] * xf;
-      if (a.intr == 3) { u0 += jk[2] * __ldg(xk + 1); u1 += jk[3] * __ldg(xk + 2); }
-    }
+    load_geom<TILE>(sm, ls, lp, g);
+    apply_Jc<TILE, ROT>(sm, ls, g, a00, a02, a12, a.intr, xk, inv_f, u0, u1, jf0, jf1, sq);
   }
   double* sv = sm.sv + tid;
+  {
+    const double d0 = a00 * u0, d1 = a00 * u1, d2 = a02 * u0 + a12 * u1;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) sv[k * TILE] = jp[0][k] * u0 + jp[1][k] * u1;
-  __syncthreads();
-  for (int pair = tid; pair < 3 * ti.np; pair += TILE) {
-    const int k = pair / ti.np, l = pair - k * ti.np;
-    const double* row = sm.sv + k * TILE;
-    double acc = 0.0;
-    for (int e = sm.pstart[l]; e < sm.pstart[l + 1]; ++e) acc += row[e];
-    sm.sw[k * TILE + l] = acc;
+    for (int k = 0; k < 3; ++k) sv[k * TILE] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
   }
+  __syncthreads();
+  const int cnp = sm.cap_np;
+  tile_reduce_points<TILE>(sm, ti, 3, [&](int k, int l, double acc) { sm.sw[k * cnp + l] = acc; });
   __syncthreads();
   double dx2 = 0.0, xc2 = 0.0;
   if (tid < ti.np) {
-    const size_t g = (size_t)ti.pt0 + tid;
-    const double t0 = sm.sw[tid], t1 = sm.sw[TILE + tid], t2 = sm.sw[2 * TILE + tid];
-    // y_p = hinv (E'r - E'F y_c) = w - hinv t ;  step_p = -y_p
-    const double y0 = wp[0] - (hp[0] * t0 + hp[1] * t1 + hp[2] * t2);
-    const double y1 = wp[1] - (hp[1] * t0 + hp[3] * t1 + hp[4] * t2);
-    const double y2 = wp[2] - (hp[2] * t0 + hp[4] * t1 + hp[5] * t2);
-    sm.sw[tid] = y0; sm.sw[TILE + tid] = y1; sm.sw[2 * TILE + tid] = y2;
-    const double d0 = -y0 * spp[0], d1 = -y1 * spp[1], d2 = -y2 * spp[2];
-    const double c0 = Xp[0] + d0, c1 = Xp[1] + d1, c2 = Xp[2] + d2;
-    a.Xc[3 * g] = c0; a.Xc[3 * g + 1] = c1; a.Xc[3 * g + 2] = c2;
-    const double e0 = Xp[0] - c0, e1 = Xp[1] - c1, e2 = Xp[2] - c2;
+    const size_t gp_ = (size_t)ti.pt0 + tid;
+    const double t0 = sm.sw[tid], t1 = sm.sw[cnp + tid], t2 = sm.sw[2 * cnp + tid];
+    const double h0 = sm.spt[3 * cnp + tid], h1 = sm.spt[4 * cnp + tid], h2 = sm.spt[5 * cnp + tid],
+                 h3 = sm.spt[6 * cnp + tid], h4 = sm.spt[7 * cnp + tid], h5 = sm.spt[8 * cnp + tid];
+    // unscaled point update: dX = -(w^ - H~ t)
+    const double y0 = sm.spt[9 * cnp + tid] - (h0 * t0 + h1 * t1 + h2 * t2);
+    const double y1 = sm.spt[10 * cnp + tid] - (h1 * t0 + h3 * t1 + h4 * t2);
+    const double y2 = sm.spt[11 * cnp + tid] - (h2 * t0 + h4 * t1 + h5 * t2);
+    sm.sw[tid] = y0; sm.sw[cnp + tid] = y1; sm.sw[2 * cnp + tid] = y2;
+    const double X0 = sm.spt[tid], X1 = sm.spt[cnp + tid], X2 = sm.spt[2 * cnp + tid];
+    const double c0 = X0 + (-y0), c1 = X1 + (-y1), c2 = X2 + (-y2);
+    a.Xc[3 * gp_] = c0; a.Xc[3 * gp_ + 1] = c1; a.Xc[3 * gp_ + 2] = c2;
+    const double e0 = X0 - c0, e1 = X1 - c1, e2 = X2 - c2;
     dx2 = e0 * e0 + e1 * e1 + e2 * e2;
     xc2 = c0 * c0 + c1 * c1 + c2 * c2;
   }
   __syncthreads();
-  // model residual of this observation: m = J * step = -(u + E y_p)
+  // model residual of this observation: m = J step = -(u + E y_p)
   double mm = 0.0;
   if (act) {
-    const double y0 = sm.sw[lp], y1 = sm.sw[TILE + lp], y2 = sm.sw[2 * TILE + lp];
-    const double m0 = -(u0 + jp[0][0] * y0 + jp[0][1] * y1 + jp[0][2] * y2);
-    const double m1 = -(u1 + jp[1][0] * y0 + jp[1][1] * y1 + jp[1][2] * y2);
+    const double z0 = sm.sw[lp], z1 = sm.sw[cnp + lp], z2 = sm.sw[2 * cnp + lp];
+    const double y0 = g.R[0] * z0 + g.R[1] * z1 + g.R[2] * z2;
+    const double y1 = g.R[3] * z0 + g.R[4] * z1 + g.R[5] * z2;
+    const double y2 = g.R[6] * z0 + g.R[7] * z1 + g.R[8] * z2;
+    const double m0 = -(u0 + a00 * y0 + a02 * y2);
+    const double m1 = -(u1 + a00 * y1 + a12 * y2);
     mm = m0 * (r0 + 0.5 * m0) + m1 * (r1 + 0.5 * m1);
   }
   double v[3] = {mm, dx2, xc2};
@@ -817,7 +847,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_back_substitute
 // ------------------------------------------------------------------ K6: cost only
 
 struct CostArgs {
-  const double* pose;
+  const double* pose;   // [F*8] q(4) t(3) pad
   const double* X;
   const double* K;
   LossP loss;
@@ -830,13 +860,16 @@ __global__ void __launch_bounds__(256) k_cost(const TileCtx tc, const CostArgs a
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)tc.M; i += (size_t)gridDim.x * 256) {
     const int img = tc.obs_img[i], pt = tc.obs_pt[i], cam = tc.img_cam[img];
     const double2 xy = tc.obs_xy[i];
-    double q[4], t[3];
-    load_pose(a.pose, img, q, t);
-    const double X[3] = {a.X[3 * (size_t)pt], a.X[3 * (size_t)pt + 1], a.X[3 * (size_t)pt + 2]};
-    Proj pr;
-    project(q, t, X, pr);
+    const double2* pp = reinterpret_cast<const double2*>(a.pose + 8 * (size_t)img);
+    const double2 qa = __ldg(pp), qb = __ldg(pp + 1), ta = __ldg(pp + 2), tb = __ldg(pp + 3);
+    const double q0 = qa.x, q1 = qa.y, q2 = qb.x, q3 = qb.y;
+    const double X0 = a.X[3 * (size_t)pt], X1 = a.X[3 * (size_t)pt + 1], X2 = a.X[3 * (size_t)pt + 2];
+    const double p0 = (1.0 - 2.0 * (q2 * q2 + q3 * q3)) * X0 + 2.0 * (q1 * q2 - q0 * q3) * X1 + 2.0 * (q1 * q3 + q0 * q2) * X2 + ta.x;
+    const double p1 = 2.0 * (q1 * q2 + q0 * q3) * X0 + (1.0 - 2.0 * (q1 * q1 + q3 * q3)) * X1 + 2.0 * (q2 * q3 - q0 * q1) * X2 + ta.y;
+    const double p2 = 2.0 * (q1 * q3 - q0 * q2) * X0 + 2.0 * (q2 * q3 + q0 * q1) * X1 + (1.0 - 2.0 * (q1 * q1 + q2 * q2)) * X2 + tb.x;
+    const double iz = 1.0 / p2;
     const double f = a.K[3 * cam], cx = a.K[3 * cam + 1], cy = a.K[3 * cam + 2];
-    const double e0 = f * pr.u + cx - xy.x, e1 = f * pr.v + cy - xy.y;
+    const double e0 = f * p0 * iz + cx - xy.x, e1 = f * p1 * iz + cy - xy.y;
     double rho0, rho1;
     loss_eval(a.loss, e0 * e0 + e1 * e1, rho0, rho1);
     cost += 0.5 * rho0;

@@ -44,17 +44,38 @@ __global__ void k_fill(double* p, double v, size_t n) {
 }
 
 // dst[i] (+)= sum over replicas of src[r][i]; the replicas are zeroed for the next use
-__global__ void k_fold_replicas(double* dst, double* rep, size_t n, size_t stride, int nrep, int accumulate,
+__global__ void k_fold_replicas(double* dst, double* rep, size_t n, size_t stride, int nrep, const double* scale,
                                 const int* skip_flag) {
   if (skip_flag && *skip_flag != 0) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double s = accumulate ? dst[i] : 0.0;
+  double s = 0.0;
   for (int r = 0; r < nrep; ++r) {
     s += rep[(size_t)r * stride + i];
     rep[(size_t)r * stride + i] = 0.0;
   }
-  dst[i] = s;
+  dst[i] = scale ? scale[i] * s : s;
+}
+
+// xs = s o x  (the tile kernels work with the unscaled Jacobian: J_scaled x = J (s o x))
+__global__ void k_scale_vec(const double* x, const double* scale, size_t n, double* xs, const int* skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xs[i] = scale[i] * x[i];
+}
+
+// pose (q, t) -> pose16 rows: R (row-major 9), t (3), pad
+__global__ void k_pose_table(const double* pose, int F, double* pose16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F) return;
+  const double* p = pose + 8 * (size_t)i;
+  const double q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+  double* o = pose16 + 16 * (size_t)i;
+  o[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3); o[1] = 2.0 * (q1 * q2 - q0 * q3); o[2] = 2.0 * (q1 * q3 + q0 * q2);
+  o[3] = 2.0 * (q1 * q2 + q0 * q3); o[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3); o[5] = 2.0 * (q2 * q3 - q0 * q1);
+  o[6] = 2.0 * (q1 * q3 - q0 * q2); o[7] = 2.0 * (q2 * q3 + q0 * q1); o[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+  o[9] = p[4]; o[10] = p[5]; o[11] = p[6];
+  o[12] = o[13] = o[14] = o[15] = 0.0;
 }
 
 // sum of squares of a vector (grid-stride), atomically added to *out
@@ -121,6 +142,7 @@ struct CamFinArgs {
   const double* prep_cam;   // [F][NVL]  -(W hinv W') blocks, -(W w)
   const double* prep_intr;  // [C][NVI]
   const unsigned char* active;  // [NS]
+  const double* scale_c;        // [NS] jacobi scaling (0 on inactive slots)
   double radius, min_diag, max_diag;
   int F, C;
   double* Dc2;    // [NS] LM diagonal squared (0 on inactive slots)
@@ -151,43 +173,45 @@ __global__ void k_cam_finalize(const CamFinArgs a) {
     slot0 = 6 * a.F + 3 * c;
   }
   const unsigned char* act = a.active + slot0;
+  const double* sc = a.scale_c + slot0;
   const int dg[3] = {0, 3, 5};
+  // the tile kernels accumulate with the UNSCALED Jacobian: apply diag(s) on both sides here
+  const double ss[6] = {sc[0] * sc[0], sc[0] * sc[1], sc[0] * sc[2], sc[1] * sc[1], sc[1] * sc[2], sc[2] * sc[2]};
   double Mb[6];
-  for (int k = 0; k < 6; ++k) Mb[k] = A[k] + Cc[k];
+  for (int k = 0; k < 6; ++k) Mb[k] = ss[k] * (A[k] + Cc[k]);
   for (int j = 0; j < 3; ++j) {
     double d2 = 0.0;
-    if (act[j]) d2 = fmin(fmax(A[dg[j]], a.min_diag), a.max_diag) / a.radius;
+    if (act[j]) d2 = fmin(fmax(ss[dg[j]] * A[dg[j]], a.min_diag), a.max_diag) / a.radius;
     a.Dc2[slot0 + j] = d2;
     Mb[dg[j]] += d2;
-    a.rhs[slot0 + j] = act[j] ? g[j] + gc[j] : 0.0;
+    a.rhs[slot0 + j] = act[j] ? sc[j] * (g[j] + gc[j]) : 0.0;
   }
   inv3_masked(Mb, act, a.Minv + (size_t)nb * 9);
 }
 
 // gradient_max_norm contribution of the camera-side blocks: |Plus(x, -g) - x|_inf with
-// g = (J_scaled' r) / scale the unscaled tangent gradient
-__global__ void k_cam_gmax(const double* lin_cam, const double* lin_intr, const double* scale_c,
+// g = J' r the (unscaled) tangent gradient
+__global__ void k_cam_gmax(const double* lin_cam, const double* lin_intr,
                            const unsigned char* active, const double* pose, int F, int C, double* gmax) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   double m = 0.0;
   if (j < F) {
     const double* g = lin_cam + (size_t)j * NVL + 12;
     const unsigned char* act = active + 6 * (size_t)j;
-    const double* sc = scale_c + 6 * (size_t)j;
     if (act[0]) {
-      const double d[3] = {-g[0] / sc[0], -g[1] / sc[1], -g[2] / sc[2]};
+      const double d[3] = {-g[0], -g[1], -g[2]};
       const double* q = pose + 8 * (size_t)j;
       double qn[4];
       quat_plus(q, d, qn);
       for (int k = 0; k < 4; ++k) m = fmax(m, fabs(q[k] - qn[k]));
     }
     for (int k = 0; k < 3; ++k)
-      if (act[3 + k]) m = fmax(m, fabs(g[3 + k] / sc[3 + k]));
+      if (act[3 + k]) m = fmax(m, fabs(g[3 + k]));
   } else if (j < F + C) {
     const int c = j - F;
     const double* g = lin_intr + (size_t)c * NVI + 6;
     for (int k = 0; k < 3; ++k)
-      if (active[6 * (size_t)F + 3 * c + k]) m = fmax(m, fabs(g[k] / scale_c[6 * (size_t)F + 3 * c + k]));
+      if (active[6 * (size_t)F + 3 * c + k]) m = fmax(m, fabs(g[k]));
   }
   if (m > 0.0) atomic_max_nonneg(gmax, m);
 }

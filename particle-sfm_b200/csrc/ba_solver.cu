@@ -82,8 +82,7 @@ struct psfm_ba_solver {
   DBuf<double> d_pose[2], d_X[2], d_K[2];
   int cur = 0;
   // linearisation
-  DBuf<double> d_r, d_jc, d_jp, d_jk, d_hpp, d_gp, d_wk, d_hinv, d_w, d_scale_c, d_scale_p;
-  size_t jc_rows = 0, jk_rows = 0;
+  DBuf<double> d_r, d_a, d_pose16, d_xs, d_hpp, d_gp, d_wk, d_hinv, d_w, d_scale_c, d_scale_p;
   // reduced system / PCG
   DBuf<double> d_lin, d_prep, d_step, d_rep, d_gmax, d_x2, d_Dc2, d_Minv, d_rhs, d_x, d_rv, d_p, d_z, d_y, d_zero;
   DBuf<double> d_camrep, d_yrep;   // [NREP] replicas of the per-image accumulators (see ba_kernels.cuh)
@@ -97,6 +96,7 @@ struct psfm_ba_solver {
     TileCtx t;
     t.tile_start = d_tile_start.p; t.tile_pt = d_tile_pt.p; t.pt_ptr = d_pt_ptr.p;
     t.obs_img = d_obs_img.p; t.obs_pt = d_obs_pt.p; t.obs_xy = d_obs_xy.p;
+    t.obs_lseg = d_obs_lseg.p; t.obs_lpt = d_obs_lpt.p; t.cap_ns = cap_ns; t.cap_np = cap_np;
     t.tile_perm = d_tile_perm.p; t.cseg_ptr = d_cseg_ptr.p; t.cseg_img = d_cseg_img.p;
     t.cseg_off = d_cseg_off.p; t.img_cam = d_img_cam.p;
     t.F = F; t.P = P; t.M = M; t.C = C; t.T = T;
@@ -286,8 +286,8 @@ void alloc_work(psfm_ba_solver* S) {
   const size_t M = S->M, P = S->P, F = S->F, C = S->C, NS = S->NS;
   S->d_active.alloc(NS, S->stream);
   for (int k = 0; k < 2; ++k) { S->d_pose[k].alloc(8 * F, S->stream); S->d_X[k].alloc(3 * P, S->stream); S->d_K[k].alloc(3 * C, S->stream); }
-  S->d_r.alloc(2 * M, S->stream); S->d_jp.alloc(6 * M, S->stream);
-  S->jc_rows = 0; S->jk_rows = 0;   // d_jc / d_jk sized on first run (depends on options)
+  S->d_r.alloc(2 * M, S->stream); S->d_a.alloc(3 * M, S->stream);
+  S->d_pose16.alloc(16 * F, S->stream); S->d_xs.alloc(NS, S->stream);
   S->d_hpp.alloc(6 * P, S->stream); S->d_gp.alloc(3 * P, S->stream); S->d_wk.alloc(9 * P, S->stream); S->d_hinv.alloc(6 * P, S->stream); S->d_w.alloc(3 * P, S->stream);
   S->d_scale_c.alloc(NS, S->stream); S->d_scale_p.alloc(3 * P, S->stream);
   S->d_lin.alloc(F * NVL + C * NVI + 1, S->stream);
@@ -305,19 +305,19 @@ void alloc_work(psfm_ba_solver* S) {
 
 // ---------------------------------------------------------------- kernel dispatch
 
-#define PSFM_TILE_LAUNCH(KERNEL, NV, S, ROT, ARGS)                                                         \
+#define PSFM_TILE_LAUNCH(KERNEL, NV, NPT, S, ROT, ARGS)                                                    \
   do {                                                                                                     \
     const TileCtx _tc = (S)->tc();                                                                         \
     if ((S)->T > 0) {                                                                                      \
       auto _go = [&](auto tile_c, auto rot_c) {                                                            \
         constexpr int TL = decltype(tile_c)::value;                                                        \
         constexpr bool RT = decltype(rot_c)::value;                                                        \
-        const size_t smem = TileSmem<TL, NV>::bytes();                                                     \
-        static bool attr_set = false;                                                                      \
-        if (!attr_set) {                                                                                   \
+        const size_t smem = TileSmem<TL>::bytes(NV, NPT, (S)->cap_ns, (S)->cap_np);                        \
+        static size_t attr_bytes = 0;                                                                      \
+        if (smem > attr_bytes) {                                                                           \
           PSFM_CUDA(cudaFuncSetAttribute(KERNEL<TL, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                          (int)smem));                                                      \
-          attr_set = true;                                                                                 \
+          attr_bytes = smem;                                                                               \
         }                                                                                                  \
         KERNEL<TL, RT><<<(S)->T, TL, smem, (S)->stream>>>(_tc, ARGS);                                       \
       };                                                                                                   \
@@ -414,16 +414,10 @@ void download_state(psfm_ba_solver* S) {
     for (int k = 0; k < 3; ++k) S->h_xyz[3 * (size_t)S->pt_orig[id] + k] = X[3 * (size_t)id + k];
 }
 
-Jac jac_of(psfm_ba_solver* S) {
-  Jac J;
-  J.r = S->d_r.p; J.jc = S->d_jc.p; J.jp = S->d_jp.p; J.jk = S->d_jk.p;
-  return J;
-}
-
-void ensure_jac(psfm_ba_solver* S, const RunCfg& c) {
-  const size_t rows = c.rot ? 12 : 6, krows = c.intr == 3 ? 4 : (c.intr == 1 ? 2 : 0);
-  if (S->jc_rows < rows || !S->d_jc.p) { S->d_jc.alloc(rows * (size_t)S->M, S->stream); S->jc_rows = rows; }
-  if (S->jk_rows < krows || !S->d_jk.p) { S->d_jk.alloc(std::max<size_t>(krows, 1) * (size_t)S->M, S->stream); S->jk_rows = krows; }
+Lin lin_of(psfm_ba_solver* S) {
+  Lin L;
+  L.r = S->d_r.p; L.a = S->d_a.p;
+  return L;
 }
 
 template <typename T>
@@ -431,28 +425,29 @@ void d2h(psfm_ba_solver* S, T* dst, const T* src, size_t n) {
   PSFM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, S->stream));
 }
 
-void fold_replicas(psfm_ba_solver* S, double* dst, double* rep, size_t n, const int* skip_flag) {
-  k_fold_replicas<<<(unsigned)((n + 255) / 256), 256, 0, S->stream>>>(dst, rep, n, n, NREP, 0, skip_flag);
+void fold_replicas(psfm_ba_solver* S, double* dst, double* rep, size_t n, const double* scale, const int* skip_flag) {
+  k_fold_replicas<<<(unsigned)((n + 255) / 256), 256, 0, S->stream>>>(dst, rep, n, n, NREP, scale, skip_flag);
   PSFM_LAUNCH_CHECK();
 }
 
 // Jacobian sweep at the current state (r, J, E'E, E'r, F'F blocks, F'r, cost)
 void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
   S->d_lin.zero(S->stream);
+  k_pose_table<<<(S->F + 127) / 128, 128, 0, S->stream>>>(S->d_pose[S->cur].p, S->F, S->d_pose16.p);
+  PSFM_LAUNCH_CHECK();
   LinArgs a;
-  a.pose = S->d_pose[S->cur].p; a.X = S->d_X[S->cur].p; a.K = S->d_K[S->cur].p;
-  a.scale_c = S->d_scale_c.p; a.scale_p = S->d_scale_p.p;
+  a.pose16 = S->d_pose16.p; a.X = S->d_X[S->cur].p; a.K = S->d_K[S->cur].p;
   a.loss.type = c.o.loss_function_type; a.loss.a = c.o.loss_function_scale;
   a.intr = c.intr;
-  a.J = jac_of(S);
+  a.L = lin_of(S);
   a.hpp = S->d_hpp.p; a.gp = S->d_gp.p; a.wk = S->d_wk.p;
   a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL; a.acc_intr = S->d_lin.p + (size_t)S->F * NVL;
   a.acc_cost = S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
-  PSFM_TILE_LAUNCH(k_linearize, 18, S, c.rot, a);
+  PSFM_TILE_LAUNCH(k_linearize, 18, 3, S, c.rot, a);
   if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_lin.push_back({e0, e1}); }
-  fold_replicas(S, S->d_lin.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr);
+  fold_replicas(S, S->d_lin.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr, nullptr);
   dist::allreduce_sum(S->d_lin.p, S->d_lin.n, S->stream);
 }
 
@@ -463,7 +458,7 @@ void do_point_blocks(psfm_ba_solver* S, const RunCfg& c, double radius) {
   a.hpp = S->d_hpp.p; a.gp = S->d_gp.p; a.wk = S->d_wk.p; a.scale_p = S->d_scale_p.p;
   a.radius = radius; a.min_diag = c.o.min_lm_diagonal; a.max_diag = c.o.max_lm_diagonal;
   a.intr = c.intr; a.P = S->P;
-  a.hinv = S->d_hinv.p; a.w = S->d_w.p;
+  a.ht = S->d_hinv.p; a.wt = S->d_w.p;
   a.acc_intr = S->d_prep.p + (size_t)S->F * NVL;
   a.acc_fail = S->d_prep.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
   a.gmax = S->d_gmax.p;
@@ -473,7 +468,7 @@ void do_point_blocks(psfm_ba_solver* S, const RunCfg& c, double radius) {
 
 void do_cam_gmax(psfm_ba_solver* S) {
   const int n = S->F + S->C;
-  k_cam_gmax<<<(n + 127) / 128, 128, 0, S->stream>>>(S->d_lin.p, S->d_lin.p + (size_t)S->F * NVL, S->d_scale_c.p,
+  k_cam_gmax<<<(n + 127) / 128, 128, 0, S->stream>>>(S->d_lin.p, S->d_lin.p + (size_t)S->F * NVL,
                                                      S->d_active.p, S->d_pose[S->cur].p, S->F, S->C, S->d_gmax.p);
   PSFM_LAUNCH_CHECK();
 }
@@ -483,28 +478,36 @@ void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius) {
   S->d_prep.zero(S->stream);
   do_point_blocks(S, c, radius);
   PrepArgs a;
-  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.w = S->d_w.p; a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL;
-  PSFM_TILE_LAUNCH(k_schur_prep, 18, S, c.rot, a);
-  fold_replicas(S, S->d_prep.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr);
+  a.L = lin_of(S); a.pose16 = S->d_pose16.p; a.X = S->d_X[S->cur].p; a.ht = S->d_hinv.p; a.wt = S->d_w.p;
+  a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL;
+  PSFM_TILE_LAUNCH(k_schur_prep, 18, 12, S, c.rot, a);
+  fold_replicas(S, S->d_prep.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr, nullptr);
   dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
   CamFinArgs f;
   f.lin_cam = S->d_lin.p; f.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
   f.prep_cam = S->d_prep.p; f.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
-  f.active = S->d_active.p; f.radius = radius; f.min_diag = c.o.min_lm_diagonal; f.max_diag = c.o.max_lm_diagonal;
+  f.active = S->d_active.p; f.scale_c = S->d_scale_c.p; f.radius = radius; f.min_diag = c.o.min_lm_diagonal; f.max_diag = c.o.max_lm_diagonal;
   f.F = S->F; f.C = S->C; f.Dc2 = S->d_Dc2.p; f.Minv = S->d_Minv.p; f.rhs = S->d_rhs.p;
   k_cam_finalize<<<(S->NB + 127) / 128, 128, 0, S->stream>>>(f);
   PSFM_LAUNCH_CHECK();
 }
 
+void scale_vec(psfm_ba_solver* S, const double* x, const int* skip_flag) {
+  k_scale_vec<<<(S->NS + 255) / 256, 256, 0, S->stream>>>(x, S->d_scale_c.p, (size_t)S->NS, S->d_xs.p, skip_flag);
+  PSFM_LAUNCH_CHECK();
+}
+
 void do_schur_product(psfm_ba_solver* S, const RunCfg& c, const double* x, bool timed) {
+  const int* flag = &S->d_pcg.p->flag;
+  scale_vec(S, x, flag);
   SpArgs a;
-  a.J = jac_of(S); a.hinv = S->d_hinv.p; a.x = x; a.y = S->d_yrep.p; a.rep_stride = (size_t)S->NS;
-  a.flag = &S->d_pcg.p->flag; a.intr = c.intr;
+  a.L = lin_of(S); a.pose16 = S->d_pose16.p; a.X = S->d_X[S->cur].p; a.ht = S->d_hinv.p; a.xs = S->d_xs.p;
+  a.y = S->d_yrep.p; a.rep_stride = (size_t)S->NS; a.flag = flag; a.K = S->d_K[S->cur].p; a.intr = c.intr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
-  PSFM_TILE_LAUNCH(k_schur_product, 6, S, c.rot, a);
+  PSFM_TILE_LAUNCH(k_schur_product, 6, 9, S, c.rot, a);
   if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_sp.push_back({e0, e1}); }
-  fold_replicas(S, S->d_y.p, S->d_yrep.p, (size_t)S->NS, &S->d_pcg.p->flag);
+  fold_replicas(S, S->d_y.p, S->d_yrep.p, (size_t)S->NS, S->d_scale_c.p, flag);
   dist::allreduce_sum(S->d_y.p, S->d_y.n, S->stream);
 }
 
@@ -601,8 +604,11 @@ double current_x_sqnorm(psfm_ba_solver* S) {
 struct LinOut { double cost, gmax; };
 
 // EvaluateGradientAndJacobian + the quantities the loop head needs
-LinOut linearize_and_measure(psfm_ba_solver* S, const RunCfg& c, double radius, bool timed) {
+LinOut linearize_and_measure(psfm_ba_solver* S, const RunCfg& c, double radius, bool timed, bool first = false) {
   do_linearize(S, c, timed);
+  // the sweep accumulates with the unscaled Jacobian, so the iteration-0 column norms that
+  // define Ceres' jacobi scaling come from the same sweep (no second linearisation)
+  if (first && c.o.jacobi_scaling) compute_jacobi_scaling(S);
   S->d_gmax.zero(S->stream);
   S->d_prep.zero(S->stream);
   do_point_blocks(S, c, radius);
@@ -642,10 +648,11 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   // candidate: points (inside the back-substitution), poses/intrinsics, cost
   S->d_step.zero(S->stream);
   S->d_rep.zero(S->stream);
+  scale_vec(S, S->d_x.p, nullptr);
   BackArgs b;
-  b.J = jac_of(S); b.hinv = S->d_hinv.p; b.w = S->d_w.p; b.yc = S->d_x.p; b.scale_p = S->d_scale_p.p;
-  b.X = S->d_X[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
-  PSFM_TILE_LAUNCH(k_back_substitute, 6, S, c.rot, b);
+  b.L = lin_of(S); b.pose16 = S->d_pose16.p; b.X = S->d_X[S->cur].p; b.ht = S->d_hinv.p; b.wt = S->d_w.p;
+  b.xs = S->d_xs.p; b.K = S->d_K[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
+  PSFM_TILE_LAUNCH(k_back_substitute, 3, 12, S, c.rot, b);
   ApplyArgs a;
   a.yc = S->d_x.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
   a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
@@ -728,7 +735,6 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
     return PSFM_ZERO_RESIDUALS;
   }
   const double t0 = now_s();
-  ensure_jac(S, c);
   S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
   upload_state(S);
   set_masks_and_unit_scale(S, c);
@@ -744,11 +750,7 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
   int num_invalid = 0, iteration = 0, nprod = 0;
   // iteration 0: evaluate; jacobi scaling from the unscaled Jacobian, then re-linearise scaled
   LinOut lo;
-  if (o.jacobi_scaling) {
-    do_linearize(S, c, false);
-    compute_jacobi_scaling(S);
-  }
-  lo = linearize_and_measure(S, c, radius, true);
+  lo = linearize_and_measure(S, c, radius, true, true);
   s.num_linearize = 1;
   double x_cost = lo.cost, gmax = lo.gmax;
   double x_norm = std::sqrt(current_x_sqnorm(S));
@@ -967,8 +969,7 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
     RunCfg c;
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
-    ensure_jac(S, c);
-    upload_state(S);
+      upload_state(S);
     set_masks_and_unit_scale(S, c);
     do_linearize(S, c, false);
     const size_t F = S->F, C = S->C, M = S->M, P = S->P;
@@ -987,9 +988,10 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
       }
     if (gradient_cam) {
       for (size_t i = 0; i < F; ++i)
-        for (int k = 0; k < 6; ++k) gradient_cam[6 * i + k] = lin[i * NVL + 12 + k];
+        for (int k = 0; k < 6; ++k) gradient_cam[6 * i + k] = c.active[6 * i + k] ? lin[i * NVL + 12 + k] : 0.0;
       for (size_t cc = 0; cc < C; ++cc)
-        for (int k = 0; k < 3; ++k) gradient_cam[6 * F + 3 * cc + k] = lin[F * NVL + cc * NVI + 6 + k];
+        for (int k = 0; k < 3; ++k)
+          gradient_cam[6 * F + 3 * cc + k] = c.active[6 * F + 3 * cc + k] ? lin[F * NVL + cc * NVI + 6 + k] : 0.0;
     }
     if (gradient_pts) {
       memset(gradient_pts, 0, sizeof(double) * 3 * (size_t)S->P_total);
@@ -1009,12 +1011,10 @@ extern "C" int psfm_ba_linear_step(psfm_ba_solver* S, const psfm_ba_options* opt
     RunCfg c;
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
-    ensure_jac(S, c);
-    S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
+      S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
     upload_state(S);
     set_masks_and_unit_scale(S, c);
-    if (c.o.jacobi_scaling) { do_linearize(S, c, false); compute_jacobi_scaling(S); }
-    linearize_and_measure(S, c, radius, false);
+    linearize_and_measure(S, c, radius, false, true);
     int nprod = 0;
     const StepOut so = compute_step(S, c, radius, &nprod);
     const size_t NS = S->NS, P = S->P;
