@@ -1,0 +1,363 @@
+// ba_schur_explicit.cuh — EXACT reduced-camera-system solve on the device.
+//
+// The reference solves the reduced camera system exactly for <= 1000 images (DENSE_SCHUR /
+// SPARSE_SCHUR, bundle_adjustment.cc:276-286): Ceres' SchurEliminator forms
+//     S = F'F + D_c^2 - sum_p (F'E)_p (E'E + D_p^2)^-1 (E'F)_p
+// and factorises it.  This file does the same on the GPU:
+//   k_schur_w        per observation W_i = Jc_i' Jp_i (6x3) and W_i H~_p, stored AoS;
+//                    per image the rot-t cross block of F'F and the focal column terms
+//   pair structure   all (i, j) observation pairs of a point grouped by image pair (a <= b)
+//                    (built once per problem with radix sort / run-length encode)
+//   k_schur_pairs    one CTA per chunk of one image-pair block: sum_i,j (W_i H~) W_j'
+//   k_schur_assemble dense symmetric S (6F+3C)^2 with Jacobi scaling, LM diagonal, gauge
+//   k_chol_banded    in-place banded(+arrow) Cholesky and the two triangular solves,
+//                    band = 6 * (longest image span of a track) — video tracks make S banded
+// Everything accumulates with the UNSCALED factored Jacobian (see ba_kernels.cuh); the
+// scaling diag(s) is applied in k_schur_assemble.
+#pragma once
+#include <cub/cub.cuh>
+
+#include "ba_kernels.cuh"
+
+namespace psfm {
+namespace ba {
+
+constexpr int NVX = 21;   // k_schur_w per-image sums: rot-t cross block (9) | F'G focal (6) | -(W H~) Wk' (6)
+
+// ------------------------------------------------------------------ per-observation W, W H~
+
+struct SwArgs {
+  Lin L;
+  const double* pose16;
+  const double* X;
+  const double* ht;     // [6][P]
+  const double* wk;     // [9][P] G'E per point (focal row used)
+  const double* K;
+  double* W;            // [M][18]  rows: rot 0..2, t 0..2 ; 3 values per row
+  double* WH;           // [M][18]
+  double* acc_cam;      // [NREP][F][NVX]
+  size_t rep_stride;
+  int intr;
+};
+
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_w(const TileCtx tc, const SwArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, NVX, 12, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
+  const int tid = threadIdx.x;
+  const bool act = tid < ti.n;
+  const size_t M = tc.M;
+  const size_t i = (size_t)ti.base + tid;
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0;
+  if (act) {
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
+  }
+  const double inv_f = (a.intr >= 1) ? 1.0 / __ldg(a.K) : 0.0;
+  // per point: X (0..2), H~ (3..8), focal row of G'E (9..11)
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wk, true);
+  double* sv = sm.sv + tid;
+#pragma unroll
+  for (int k = 0; k < NVX; ++k) sv[k * TILE] = 0.0;
+  if (act) {
+    ObsGeom g;
+    load_geom<TILE>(sm, ls, lp, g);
+    const int cnp = sm.cap_np;
+    double hv[6], wkp[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wkp[k] = sm.spt[(9 + k) * cnp + lp];
+    double jp[2][3], jc[2][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      jp[0][k] = a00 * g.R[k] + a02 * g.R[6 + k];
+      jp[1][k] = a00 * g.R[3 + k] + a12 * g.R[6 + k];
+    }
+    if (ROT) {
+      jc[0][0] = 2.0 * a02 * g.w[1]; jc[0][1] = 2.0 * (a00 * g.w[2] - a02 * g.w[0]); jc[0][2] = -2.0 * a00 * g.w[1];
+      jc[1][0] = 2.0 * (a12 * g.w[1] - a00 * g.w[2]); jc[1][1] = -2.0 * a12 * g.w[0]; jc[1][2] = 2.0 * a00 * g.w[0];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { jc[0][k] = 0.0; jc[1][k] = 0.0; }
+    }
+    jc[0][3] = a00; jc[0][4] = 0.0; jc[0][5] = a02;
+    jc[1][3] = 0.0; jc[1][4] = a00; jc[1][5] = a12;
+    double W[6][3], WH[6][3];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) W[r][k] = jc[0][r] * jp[0][k] + jc[1][r] * jp[1][k];
+      WH[r][0] = W[r][0] * hv[0] + W[r][1] * hv[1] + W[r][2] * hv[2];
+      WH[r][1] = W[r][0] * hv[1] + W[r][1] * hv[3] + W[r][2] * hv[4];
+      WH[r][2] = W[r][0] * hv[2] + W[r][1] * hv[4] + W[r][2] * hv[5];
+    }
+    double2* Wo = reinterpret_cast<double2*>(a.W + 18 * i);
+    double2* WHo = reinterpret_cast<double2*>(a.WH + 18 * i);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      Wo[k] = make_double2(W[(2 * k) / 3][(2 * k) % 3], W[(2 * k + 1) / 3][(2 * k + 1) % 3]);
+      WHo[k] = make_double2(WH[(2 * k) / 3][(2 * k) % 3], WH[(2 * k + 1) / 3][(2 * k + 1) % 3]);
+    }
+    // rot-t cross block of F'F: (Jr' Jt)[r][c]
+    if (ROT) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * TILE] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
+    }
+    if (a.intr >= 1) {
+      const double zf = (g.w[2] + g.tz) * inv_f;
+      const double jf0 = -a02 * zf, jf1 = -a12 * zf;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        sv[(9 + r) * TILE] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
+        sv[(15 + r) * TILE] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
+      }
+    }
+  }
+  __syncthreads();
+  double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
+  tile_reduce_images<TILE>(sm, ti, NVX, [&](int k, int img, double acc) {
+    if (acc != 0.0) atomicAdd(dst + (size_t)img * NVX + k, acc);
+  });
+}
+
+// ------------------------------------------------------------------ pair structure
+
+// entries started by observation j (sorted order): (j, j), (j, j+1) ... (j, end of its point)
+// plus (j, j') for earlier observations j' of the same point IN THE SAME IMAGE (rare
+// duplicates: both orders are needed inside a diagonal block)
+__global__ void k_pair_count(const int* pt_ptr, const int* obs_pt, const int* obs_img, int M, int* cnt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int p = obs_pt[j];
+  const int b = pt_ptr[p], e = pt_ptr[p + 1];
+  int c = e - j;
+  for (int k = j - 1; k >= b && obs_img[k] == obs_img[j]; --k) ++c;
+  cnt[j] = c;
+}
+
+__global__ void k_pair_fill(const int* pt_ptr, const int* obs_pt, const int* obs_img, const int* ptr, int M, int F,
+                            unsigned int* keys, unsigned long long* vals) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int p = obs_pt[j];
+  const int b = pt_ptr[p], e = pt_ptr[p + 1];
+  const int a = obs_img[j];
+  size_t o = (size_t)ptr[j];
+  for (int k = j; k < e; ++k, ++o) {
+    keys[o] = (unsigned)a * (unsigned)F + (unsigned)obs_img[k];
+    vals[o] = ((unsigned long long)(unsigned)j << 32) | (unsigned)k;
+  }
+  for (int k = j - 1; k >= b && obs_img[k] == a; --k, ++o) {
+    keys[o] = (unsigned)a * (unsigned)F + (unsigned)a;
+    vals[o] = ((unsigned long long)(unsigned)j << 32) | (unsigned)k;
+  }
+}
+
+// ------------------------------------------------------------------ block products
+
+struct PairArgs {
+  const unsigned long long* entries;   // (i << 32) | j, sorted by image pair
+  const int* chunk_blk;                // [nchunks] block id
+  const long long* chunk_beg;          // [nchunks + 1] entry range of the chunk
+  const double* W;                     // [M][18]
+  const double* WH;                    // [M][18]
+  double* Sblk;                        // [nblocks][36]  += sum (W_i H~) W_j'
+};
+
+__global__ void __launch_bounds__(128) k_schur_pairs(const PairArgs a) {
+  __shared__ double sred[36 * 4];
+  const int ch = blockIdx.x;
+  const long long beg = a.chunk_beg[ch], end = a.chunk_beg[ch + 1];
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  for (long long e = beg + threadIdx.x; e < end; e += 128) {
+    const unsigned long long ij = a.entries[e];
+    const size_t i = (size_t)(ij >> 32), j = (size_t)(ij & 0xffffffffull);
+    const double2* wh = reinterpret_cast<const double2*>(a.WH + 18 * i);
+    const double2* wj = reinterpret_cast<const double2*>(a.W + 18 * j);
+    double A[18], B[18];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double2 u = __ldg(wh + k), v = __ldg(wj + k);
+      A[2 * k] = u.x; A[2 * k + 1] = u.y;
+      B[2 * k] = v.x; B[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        acc[6 * r + c] += A[3 * r] * B[3 * c] + A[3 * r + 1] * B[3 * c + 1] + A[3 * r + 2] * B[3 * c + 2];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) sred[k * 4 + wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const double s = sred[threadIdx.x * 4] + sred[threadIdx.x * 4 + 1] + sred[threadIdx.x * 4 + 2] + sred[threadIdx.x * 4 + 3];
+    atomicAdd(a.Sblk + 36 * (size_t)a.chunk_blk[ch] + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ assembly of the dense reduced system
+
+struct AsmArgs {
+  const double* Sblk;       // [nblocks][36]
+  const int* blk_key;       // [nblocks] a * F + b  (a <= b)
+  int nblocks;
+  const double* lin_cam;    // [F][NVL]  rot F'F (6) | t F'F (6) | ...
+  const double* lin_intr;   // [C][NVI]
+  const double* prep_intr;  // [C][NVI]
+  const double* xcam;       // [F][NVX]
+  const double* scale_c;    // [NS]
+  const double* Dc2;        // [NS]
+  const unsigned char* active;
+  int F, C, NS;
+  double* S;                // [NS][NS] row-major, zeroed
+};
+
+// off-diagonal / diagonal pair blocks: S[6a+r][6b+c] -= s s' Sblk (mirrored)
+__global__ void k_schur_assemble_blocks(const AsmArgs a) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)a.nblocks * 36) return;
+  const int blk = (int)(t / 36), e = (int)(t % 36), r = e / 6, c = e % 6;
+  const int ia = a.blk_key[blk] / a.F, ib = a.blk_key[blk] % a.F;
+  const size_t row = 6 * (size_t)ia + r, col = 6 * (size_t)ib + c;
+  const double v = -a.scale_c[row] * a.scale_c[col] * a.Sblk[t];
+  atomicAdd(a.S + row * a.NS + col, v);
+  if (ia != ib) atomicAdd(a.S + col * a.NS + row, v);
+}
+
+// rank-local per-image parts: rot-t cross block of F'F and the focal column
+__global__ void k_schur_assemble_local(const AsmArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NS = a.NS, F = a.F;
+  if (j >= F) return;
+  const double* X = a.xcam + (size_t)j * NVX;
+  const size_t s0 = 6 * (size_t)j;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double x = a.scale_c[s0 + r] * a.scale_c[s0 + 3 + c] * X[3 * r + c];
+      if (x != 0.0) { atomicAdd(a.S + (s0 + r) * NS + s0 + 3 + c, x); atomicAdd(a.S + (s0 + 3 + c) * NS + s0 + r, x); }
+    }
+  const size_t sk = 6 * (size_t)F;   // single shared camera when intrinsics are free
+  for (int r = 0; r < 6; ++r) {
+    const double v = a.scale_c[s0 + r] * a.scale_c[sk] * (X[9 + r] + X[15 + r]);
+    if (v != 0.0) { atomicAdd(a.S + (s0 + r) * NS + sk, v); atomicAdd(a.S + sk * NS + s0 + r, v); }
+  }
+}
+
+// parts built from already all-reduced accumulators: F'F rot/t diagonal blocks, intrinsics block
+__global__ void k_schur_assemble_global(const AsmArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NS = a.NS, F = a.F;
+  const int ut[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  if (j < F) {
+    const double* A = a.lin_cam + (size_t)j * NVL;
+    const size_t s0 = 6 * (size_t)j;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        a.S[(s0 + r) * NS + s0 + c] += a.scale_c[s0 + r] * a.scale_c[s0 + c] * A[ut[r][c]];
+        a.S[(s0 + 3 + r) * NS + s0 + 3 + c] += a.scale_c[s0 + 3 + r] * a.scale_c[s0 + 3 + c] * A[6 + ut[r][c]];
+      }
+  } else if (j < F + a.C) {
+    const int c = j - F;
+    const size_t sk = 6 * (size_t)F + 3 * c;
+    const double* G = a.lin_intr + (size_t)c * NVI;
+    const double* Gc = a.prep_intr + (size_t)c * NVI;
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc)
+        a.S[(sk + r) * NS + sk + cc] += a.scale_c[sk + r] * a.scale_c[sk + cc] * (G[ut[r][cc]] + Gc[ut[r][cc]]);
+  }
+}
+
+// LM diagonal on active slots, identity on inactive ones (their rows/cols are zero: scale 0)
+__global__ void k_schur_assemble_finish(const AsmArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.NS) return;
+  if (a.active[s]) a.S[(size_t)s * a.NS + s] += a.Dc2[s];
+  else a.S[(size_t)s * a.NS + s] = 1.0;
+}
+
+// ------------------------------------------------------------------ banded (+ arrow) Cholesky, single CTA
+
+// S is symmetric positive definite with S[i][j] == 0 for |i - j| > bw among the first nb
+// rows; the last (n - nb) rows/columns (shared intrinsics) are dense ("arrow").  In-place
+// lower factor, then L y = b, L' x = y.  fail[0] = 1 when a pivot is not positive.
+__global__ void __launch_bounds__(1024) k_chol_banded(double* S, int n, int nb, int bw, const double* b, double* x, int* fail) {
+  __shared__ double s_d;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      const double d = S[(size_t)j * n + j];
+      if (!(d > 0.0) || isinf(d)) s_bad = 1;
+      s_d = sqrt(d);
+      S[(size_t)j * n + j] = s_d;
+    }
+    __syncthreads();
+    if (s_bad) break;
+    const double dj = s_d;
+    // rows below j that can be non-zero: band rows, then the arrow rows
+    const int r1 = (j < nb) ? min(nb, j + bw + 1) : n;      // band part end (exclusive)
+    const int nband = max(0, r1 - (j + 1));
+    const int arrow0 = max(nb, j + 1);
+    const int nrows = nband + (n - arrow0) * (j < nb ? 1 : 0);
+    const int total = (j < nb) ? nrows : (n - (j + 1));
+    for (int t = tid; t < total; t += nt) {
+      const int i = (j < nb) ? (t < nband ? j + 1 + t : arrow0 + (t - nband)) : j + 1 + t;
+      S[(size_t)i * n + j] /= dj;
+    }
+    __syncthreads();
+    // trailing update (lower triangle of the active window)
+    const long long pairs = (long long)total * (total + 1) / 2;
+    for (long long q = tid; q < pairs; q += nt) {
+      // q -> (u >= v) in the triangular index space
+      int u = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+      while ((long long)(u + 1) * (u + 2) / 2 <= q) ++u;
+      while ((long long)u * (u + 1) / 2 > q) --u;
+      const int v = (int)(q - (long long)u * (u + 1) / 2);
+      const int iu = (j < nb) ? (u < nband ? j + 1 + u : arrow0 + (u - nband)) : j + 1 + u;
+      const int iv = (j < nb) ? (v < nband ? j + 1 + v : arrow0 + (v - nband)) : j + 1 + v;
+      S[(size_t)iu * n + iv] -= S[(size_t)iu * n + j] * S[(size_t)iv * n + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *fail = s_bad;
+  if (s_bad) return;
+  // forward: L y = b
+  __shared__ double sred[32];
+  for (int i = 0; i < n; ++i) {
+    const int k0 = (i < nb) ? max(0, i - bw) : 0;
+    double s = 0.0;
+    for (int k = k0 + tid; k < i; k += nt) s += S[(size_t)i * n + k] * x[k];
+    s = block_sum(s, sred);
+    if (tid == 0) x[i] = ((i < n ? b[i] : 0.0) - s) / S[(size_t)i * n + i];
+    __syncthreads();
+  }
+  // backward: L' x = y
+  for (int i = n - 1; i >= 0; --i) {
+    const int k1 = (i < nb) ? min(nb, i + bw + 1) : n;
+    double s = 0.0;
+    for (int k = i + 1 + tid; k < k1; k += nt) s += S[(size_t)k * n + i] * x[k];
+    if (i < nb) for (int k = max(nb, i + 1) + tid; k < n; k += nt) s += S[(size_t)k * n + i] * x[k];
+    s = block_sum(s, sred);
+    if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
+    __syncthreads();
+  }
+}
+
+}  // namespace ba
+}  // namespace psfm

@@ -16,6 +16,7 @@
 
 #include "ba_small_kernels.cuh"
 #include "ba_structure.cuh"
+#include "ba_schur_explicit.cuh"
 #include "dist.cuh"
 
 namespace psfm {
@@ -86,6 +87,14 @@ struct psfm_ba_solver {
   // reduced system / PCG
   DBuf<double> d_lin, d_prep, d_step, d_rep, d_gmax, d_x2, d_Dc2, d_Minv, d_rhs, d_x, d_rv, d_p, d_z, d_y, d_zero;
   DBuf<double> d_camrep, d_yrep;   // [NREP] replicas of the per-image accumulators (see ba_kernels.cuh)
+  // explicit Schur complement (exact mode, ba_schur_explicit.cuh)
+  bool pairs_ready = false;
+  int nblocks = 0, nchunks = 0, bw = 0;
+  long long npairs = 0;
+  DBuf<unsigned long long> d_entries;
+  DBuf<int> d_blk_key, d_chunk_blk, d_cholfail;
+  DBuf<long long> d_chunk_beg;
+  DBuf<double> d_W, d_WH, d_xcam, d_xcamrep, d_Sblk, d_S;
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   cudaStream_t stream = nullptr;
@@ -629,6 +638,144 @@ struct StepOut {
   double mcc, step_sq, cand_x2, cand_cost;
 };
 
+__global__ void k_point_span(const int* pt_ptr, const int* obs_img, int P, int* span_max) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int b = pt_ptr[p], e = pt_ptr[p + 1];
+  if (e > b) atomicMax(span_max, obs_img[e - 1] - obs_img[b]);
+}
+
+// (i, j) observation pairs of every point grouped by image pair — built once per problem
+void ensure_pairs(psfm_ba_solver* S) {
+  if (S->pairs_ready) return;
+  PhaseTimer tm;
+  cudaStream_t st = S->stream;
+  const int M = S->M, F = S->F;
+  DBuf<int> cnt, span;
+  DBuf<unsigned int> keys, keys_out, ukeys;
+  DBuf<unsigned long long> vals;
+  DBuf<int> ucount, nruns;
+  cnt.alloc((size_t)M + 1, st); span.alloc(1, st); span.zero(st);
+  PSFM_CUDA(cudaMemsetAsync(cnt.p + M, 0, sizeof(int), st));
+  k_pair_count<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, M, cnt.p);
+  PSFM_LAUNCH_CHECK();
+  k_point_span<<<grid_for(S->P), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_img.p, S->P, span.p);
+  PSFM_LAUNCH_CHECK();
+  // exclusive scan of the per-observation entry counts (64-bit total)
+  DBuf<long long> ptr64;
+  ptr64.alloc((size_t)M + 1, st);
+  {
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, ptr64.p, M + 1, st);
+    DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+    cub::DeviceScan::ExclusiveSum(tmp.p, need, cnt.p, ptr64.p, M + 1, st);
+    long long total = 0; int h_span = 0;
+    PSFM_CUDA(cudaMemcpyAsync(&total, ptr64.p + M, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaMemcpyAsync(&h_span, span.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->npairs = total;
+    S->bw = 6 * h_span + 5;
+  }
+  if (S->npairs >= (1ll << 31)) { set_error("too many observation pairs for the explicit Schur complement"); throw CudaFail{PSFM_ERR_UNSUPPORTED}; }
+  const size_t NPr = (size_t)S->npairs;
+  // 32-bit offsets for the fill kernel
+  DBuf<int> ptr32; ptr32.alloc((size_t)M + 1, st);
+  {
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, ptr32.p, M + 1, st);
+    DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+    cub::DeviceScan::ExclusiveSum(tmp.p, need, cnt.p, ptr32.p, M + 1, st);
+  }
+  keys.alloc(NPr, st); keys_out.alloc(NPr, st); vals.alloc(NPr, st); S->d_entries.alloc(NPr, st);
+  k_pair_fill<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, ptr32.p, M, F, keys.p, vals.p);
+  PSFM_LAUNCH_CHECK();
+  int kbits = 1; while ((1ull << kbits) < (unsigned long long)F * F) ++kbits;
+  {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys.p, keys_out.p, vals.p, S->d_entries.p, (int)NPr, 0, kbits, st);
+    DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+    cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, vals.p, S->d_entries.p, (int)NPr, 0, kbits, st);
+  }
+  // run-length encode -> image-pair blocks
+  ukeys.alloc(NPr, st); ucount.alloc(NPr, st); nruns.alloc(1, st);
+  {
+    size_t need = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, need, keys_out.p, ukeys.p, ucount.p, nruns.p, (int)NPr, st);
+    DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+    cub::DeviceRunLengthEncode::Encode(tmp.p, need, keys_out.p, ukeys.p, ucount.p, nruns.p, (int)NPr, st);
+  }
+  int nb = 0;
+  PSFM_CUDA(cudaMemcpyAsync(&nb, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  S->nblocks = nb;
+  std::vector<unsigned int> h_keys(nb);
+  std::vector<int> h_cnt(nb);
+  PSFM_CUDA(cudaMemcpyAsync(h_keys.data(), ukeys.p, sizeof(unsigned) * nb, cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaMemcpyAsync(h_cnt.data(), ucount.p, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  // chunks of <= 4096 entries of one block
+  const int CH = 4096;
+  std::vector<int> chunk_blk, blk_key(nb);
+  std::vector<long long> chunk_beg;
+  long long off = 0;
+  for (int b = 0; b < nb; ++b) {
+    blk_key[b] = (int)h_keys[b];
+    for (int c0 = 0; c0 < h_cnt[b]; c0 += CH) { chunk_blk.push_back(b); chunk_beg.push_back(off + c0); }
+    off += h_cnt[b];
+  }
+  chunk_beg.push_back(off);
+  // a chunk ends where the next begins, except at block boundaries: store explicit ends by
+  // making chunk_beg[k+1] the end of chunk k (chunks are consecutive in entry order)
+  S->nchunks = (int)chunk_blk.size();
+  S->d_blk_key.alloc(nb, st); S->d_blk_key.upload(blk_key.data(), nb, st);
+  S->d_chunk_blk.alloc(S->nchunks, st); S->d_chunk_blk.upload(chunk_blk.data(), S->nchunks, st);
+  S->d_chunk_beg.alloc((size_t)S->nchunks + 1, st); S->d_chunk_beg.upload(chunk_beg.data(), (size_t)S->nchunks + 1, st);
+  S->d_W.alloc(18 * (size_t)M, st); S->d_WH.alloc(18 * (size_t)M, st);
+  S->d_xcam.alloc((size_t)F * NVX, st); S->d_xcamrep.alloc((size_t)NREP * F * NVX, st); S->d_xcamrep.zero(st);
+  S->d_Sblk.alloc((size_t)nb * 36, st); S->d_S.alloc((size_t)S->NS * S->NS, st); S->d_cholfail.alloc(1, st);
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  S->pairs_ready = true;
+  tm.mark("pair structure (explicit Schur)");
+}
+
+// exact reduced-system solve: explicit S, banded Cholesky; solution in d_x. returns false on failure
+bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
+  ensure_pairs(S);
+  cudaStream_t st = S->stream;
+  SwArgs w;
+  w.L = lin_of(S); w.pose16 = S->d_pose16.p; w.X = S->d_X[S->cur].p; w.ht = S->d_hinv.p; w.wk = S->d_wk.p;
+  w.K = S->d_K[S->cur].p; w.W = S->d_W.p; w.WH = S->d_WH.p; w.acc_cam = S->d_xcamrep.p;
+  w.rep_stride = (size_t)S->F * NVX; w.intr = c.intr;
+  PSFM_TILE_LAUNCH(k_schur_w, NVX, 12, S, c.rot, w);
+  fold_replicas(S, S->d_xcam.p, S->d_xcamrep.p, (size_t)S->F * NVX, nullptr, nullptr);
+  S->d_Sblk.zero(st);
+  PairArgs pa;
+  pa.entries = S->d_entries.p; pa.chunk_blk = S->d_chunk_blk.p; pa.chunk_beg = S->d_chunk_beg.p;
+  pa.W = S->d_W.p; pa.WH = S->d_WH.p; pa.Sblk = S->d_Sblk.p;
+  if (S->nchunks) { k_schur_pairs<<<S->nchunks, 128, 0, st>>>(pa); PSFM_LAUNCH_CHECK(); }
+  S->d_S.zero(st);
+  AsmArgs a;
+  a.Sblk = S->d_Sblk.p; a.blk_key = S->d_blk_key.p; a.nblocks = S->nblocks;
+  a.lin_cam = S->d_lin.p; a.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
+  a.prep_intr = S->d_prep.p + (size_t)S->F * NVL; a.xcam = S->d_xcam.p;
+  a.scale_c = S->d_scale_c.p; a.Dc2 = S->d_Dc2.p; a.active = S->d_active.p;
+  a.F = S->F; a.C = S->C; a.NS = S->NS; a.S = S->d_S.p;
+  if (S->nblocks) { k_schur_assemble_blocks<<<grid_for((size_t)S->nblocks * 36), 256, 0, st>>>(a); PSFM_LAUNCH_CHECK(); }
+  k_schur_assemble_local<<<grid_for(S->F, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  dist::allreduce_sum(S->d_S.p, S->d_S.n, st);
+  k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  const int nbnd = 6 * S->F;
+  int bw = std::min(S->bw, nbnd);
+  if (dist::world_size() > 1) bw = nbnd;   // ranks may see different spans: use the dense band
+  k_chol_banded<<<1, 1024, 0, st>>>(S->d_S.p, S->NS, nbnd, bw, S->d_rhs.p, S->d_x.p, S->d_cholfail.p);
+  PSFM_LAUNCH_CHECK();
+  int fail = 0;
+  PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  return fail == 0;
+}
+
 // LevenbergMarquardtStrategy::ComputeStep + ComputeCandidatePointAndEvaluateCost
 StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* nprod) {
   StepOut so;
@@ -643,7 +790,14 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
     max_it = c.o.exact_max_iterations > 0 ? c.o.exact_max_iterations
                                           : std::min(20000, std::max(1000, 5 * S->NS));
   }
-  so.pcg_flag = do_pcg(S, c, q_tol, r_tol, max_it, &iters, nprod);
+  const bool explicit_ok = c.solver == PSFM_BA_SOLVER_EXACT_SCHUR && c.intr <= 1 && !getenv("PSFM_EXACT_PCG") &&
+                           (size_t)S->NS * S->NS * sizeof(double) <= ((size_t)4 << 30);
+  if (explicit_ok) {
+    so.pcg_flag = do_explicit_solve(S, c) ? PCG_SUCCESS : PCG_FAILURE;
+    iters = 1;
+  } else {
+    so.pcg_flag = do_pcg(S, c, q_tol, r_tol, max_it, &iters, nprod);
+  }
   so.pcg_iters = iters;
   // candidate: points (inside the back-substitution), poses/intrinsics, cost
   S->d_step.zero(S->stream);
