@@ -15,6 +15,7 @@
 // Everything accumulates with the UNSCALED factored Jacobian (see ba_kernels.cuh); the
 // scaling diag(s) is applied in k_schur_assemble.
 #pragma once
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "ba_kernels.cuh"
@@ -222,8 +223,10 @@ struct AsmArgs {
   const double* scale_c;    // [NS]
   const double* Dc2;        // [NS]
   const unsigned char* active;
+  const double* rhs;        // [NS]
   int F, C, NS;
-  double* S;                // [NS][NS] row-major, zeroed
+  int lda;                  // leading dimension of S (NS + 1: the extra row carries the rhs)
+  double* S;                // [lda][lda] row-major, zeroed
 };
 
 // off-diagonal / diagonal pair blocks: S[6a+r][6b+c] -= s s' Sblk (mirrored)
@@ -234,14 +237,14 @@ __global__ void k_schur_assemble_blocks(const AsmArgs a) {
   const int ia = a.blk_key[blk] / a.F, ib = a.blk_key[blk] % a.F;
   const size_t row = 6 * (size_t)ia + r, col = 6 * (size_t)ib + c;
   const double v = -a.scale_c[row] * a.scale_c[col] * a.Sblk[t];
-  atomicAdd(a.S + row * a.NS + col, v);
-  if (ia != ib) atomicAdd(a.S + col * a.NS + row, v);
+  atomicAdd(a.S + row * a.lda + col, v);
+  if (ia != ib) atomicAdd(a.S + col * a.lda + row, v);
 }
 
 // rank-local per-image parts: rot-t cross block of F'F and the focal column
 __global__ void k_schur_assemble_local(const AsmArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NS = a.NS, F = a.F;
+  const int NS = a.lda, F = a.F;
   if (j >= F) return;
   const double* X = a.xcam + (size_t)j * NVX;
   const size_t s0 = 6 * (size_t)j;
@@ -260,7 +263,7 @@ __global__ void k_schur_assemble_local(const AsmArgs a) {
 // parts built from already all-reduced accumulators: F'F rot/t diagonal blocks, intrinsics block
 __global__ void k_schur_assemble_global(const AsmArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int NS = a.NS, F = a.F;
+  const int NS = a.lda, F = a.F;
   const int ut[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
   if (j < F) {
     const double* A = a.lin_cam + (size_t)j * NVL;
@@ -285,8 +288,9 @@ __global__ void k_schur_assemble_global(const AsmArgs a) {
 __global__ void k_schur_assemble_finish(const AsmArgs a) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.NS) return;
-  if (a.active[s]) a.S[(size_t)s * a.NS + s] += a.Dc2[s];
-  else a.S[(size_t)s * a.NS + s] = 1.0;
+  if (a.active[s]) a.S[(size_t)s * a.lda + s] += a.Dc2[s];
+  else a.S[(size_t)s * a.lda + s] = 1.0;
+  a.S[(size_t)a.NS * a.lda + s] = a.rhs[s];      // rhs as an extra (arrow) row: its factor row is L^-1 b
 }
 
 // ------------------------------------------------------------------ banded (+ arrow) Cholesky, single CTA
@@ -355,6 +359,176 @@ __global__ void __launch_bounds__(1024) k_chol_banded(double* S, int n, int nb, 
     if (i < nb) for (int k = max(nb, i + 1) + tid; k < n; k += nt) s += S[(size_t)k * n + i] * x[k];
     s = block_sum(s, sred);
     if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
+    __syncthreads();
+  }
+}
+
+
+// ------------------------------------------------------------------ blocked, band-aware Cholesky (cooperative, multi-CTA)
+
+// In-place lower Cholesky of the leading ns x ns part of A (row-major, leading dimension
+// lda), where A[i][j] == 0 for |i - j| > bw among the first nb rows and rows nb..ns-1 are
+// dense ("arrow": shared intrinsics).  Row ns of A holds the right-hand side b: it is
+// carried through the factorisation as one more arrow row, so that afterwards
+// A[ns][k] = (L^-1 b)[k]; CTA 0 then solves L' x = L^-1 b.  One cooperative launch:
+// per 32-column panel  (1) every CTA factors the 32x32 diagonal block redundantly in shared
+// memory, (2) the rows below are solved against it, (3) grid.sync, the trailing tiles inside
+// the band are updated, grid.sync.  fail[0] = 1 when a pivot is not positive.
+constexpr int CB = 32;
+
+struct CholArgs {
+  double* A;
+  int ns, lda, nb, bw;
+  double* x;      // [ns]
+  int* fail;
+};
+
+__device__ __forceinline__ int chol_row_of(int pos, int c1, int nband, int arrow0) {
+  return pos < nband ? c1 + pos : arrow0 + (pos - nband);
+}
+
+__global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
+  namespace cgx = cooperative_groups;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double sD[CB][CB + 1];
+  __shared__ double sLi[CB][CB + 1];
+  __shared__ double sLj[CB][CB + 1];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  const int ns = a.ns, lda = a.lda, nrows = a.ns + 1;     // rows incl. the rhs row
+  double* A = a.A;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < ns; c0 += CB) {
+    const int w = min(CB, ns - c0), c1 = c0 + w;
+    // ---- (1) diagonal block, redundantly per CTA
+    for (int t = tid; t < CB * CB; t += 256) {
+      const int r = t / CB, c = t % CB;
+      sD[r][c] = (r < w && c <= r) ? A[(size_t)(c0 + r) * lda + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < w; ++j) {
+      if (tid == 0) {
+        const double d = sD[j][j];
+        if (!(d > 0.0) || isinf(d)) s_bad = 1;
+        sD[j][j] = sqrt(d);
+      }
+      __syncthreads();
+      if (s_bad) break;
+      const double dj = sD[j][j];
+      if (tid > j && tid < w) sD[tid][j] /= dj;
+      __syncthreads();
+      for (int t = tid; t < w * w; t += 256) {
+        const int r = t / w, c = t % w;
+        if (c > j && r >= c) sD[r][c] -= sD[r][j] * sD[c][j];
+      }
+      __syncthreads();
+    }
+    if (s_bad) break;     // uniform across the grid: every CTA factors the same block
+    // ---- rows below the panel that can be non-zero
+    const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
+    const int nband = max(0, rb - c1);
+    const int arrow0 = max(a.nb, c1);
+    const int npos = nband + (nrows - arrow0);
+    // ---- (2) solve X L11' = A21 for these rows (one thread per row)
+    for (int q = blockIdx.x * CB; q < npos; q += gridDim.x * CB) {
+      const int pos = q + tid;
+      if (tid < CB && pos < npos) {
+        double* row = A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0;
+        double xr[CB];
+#pragma unroll 4
+        for (int k = 0; k < w; ++k) {
+          double s = row[k];
+          for (int m = 0; m < k; ++m) s -= xr[m] * sD[k][m];
+          xr[k] = s / sD[k][k];
+        }
+        for (int k = 0; k < w; ++k) row[k] = xr[k];
+      }
+    }
+    __threadfence();
+    grid.sync();
+    // every CTA has finished reading the unfactored diagonal block: CTA 0 stores L11
+    if (blockIdx.x == 0)
+      for (int t = tid; t < w * w; t += 256) {
+        const int r = t / w, c = t % w;
+        if (c <= r) A[(size_t)(c0 + r) * lda + c0 + c] = sD[r][c];
+      }
+    // ---- (3) trailing update of the tiles below/right of the panel
+    const int ntile = (npos + CB - 1) / CB;
+    const int npair = ntile * (ntile + 1) / 2;
+    for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) {
+      int ti = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
+      while (ti * (ti + 1) / 2 > pr) --ti;
+      const int tj = pr - ti * (ti + 1) / 2;
+      __syncthreads();
+      for (int t = tid; t < CB * CB; t += 256) {
+        const int r = t / CB, c = t % CB;
+        const int pi = ti * CB + r, pj = tj * CB + r;
+        sLi[r][c] = (pi < npos && c < w) ? A[(size_t)chol_row_of(pi, c1, nband, arrow0) * lda + c0 + c] : 0.0;
+        sLj[r][c] = (pj < npos && c < w) ? A[(size_t)chol_row_of(pj, c1, nband, arrow0) * lda + c0 + c] : 0.0;
+      }
+      __syncthreads();
+      for (int t = tid; t < CB * CB; t += 256) {
+        const int r = t / CB, c = t % CB;
+        const int pi = ti * CB + r, pj = tj * CB + c;
+        if (pi < npos && pj < npos && pj <= pi) {
+          const int gi = chol_row_of(pi, c1, nband, arrow0), gj = chol_row_of(pj, c1, nband, arrow0);
+          if (gj < ns) {       // the rhs row has no column
+            double s = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < CB; ++k) s += sLi[r][k] * sLj[c][k];
+            A[(size_t)gi * lda + gj] -= s;
+          }
+        }
+      }
+    }
+    __threadfence();
+    grid.sync();
+  }
+  if (blockIdx.x != 0) return;
+  if (tid == 0) *a.fail = s_bad;
+  if (s_bad) return;
+  // ---- back substitution L' x = y, y = A[ns][0..ns)   (CTA 0, panel by panel from the end)
+  __shared__ double sacc[8][CB];
+  for (int k = tid; k < ns; k += 256) a.x[k] = A[(size_t)ns * lda + k];
+  __syncthreads();
+  const int npanel = (ns + CB - 1) / CB;
+  for (int p = npanel - 1; p >= 0; --p) {
+    const int c0 = p * CB, w = min(CB, ns - c0), c1 = c0 + w;
+    const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
+    const int nband = max(0, rb - c1);
+    const int arrow0 = max(a.nb, c1);
+    const int npos = nband + (ns - arrow0);          // rhs row excluded
+    // partial sums: column c of the panel, rows strided over the 8 row-groups
+    const int c = tid % CB, g = tid / CB;
+    double s = 0.0;
+    if (c < w)
+      for (int pos = g; pos < npos; pos += 8) {
+        const int r = chol_row_of(pos, c1, nband, arrow0);
+        s += A[(size_t)r * lda + c0 + c] * a.x[r];
+      }
+    sacc[g][c] = s;
+    __syncthreads();
+    if (tid < w) {
+      double t = 0.0;
+      for (int gg = 0; gg < 8; ++gg) t += sacc[gg][tid];
+      sacc[0][tid] = a.x[c0 + tid] - t;
+    }
+    __syncthreads();
+    // in-panel backward substitution (warp 0)
+    if (tid < CB) {
+      for (int j = w - 1; j >= 0; --j) {
+        double v = 0.0;
+        if (tid == j) {
+          v = sacc[0][j] / A[(size_t)(c0 + j) * lda + c0 + j];
+          a.x[c0 + j] = v;
+        }
+        v = __shfl_sync(0xffffffffu, v, j);
+        if (tid < j) sacc[0][tid] -= A[(size_t)(c0 + j) * lda + c0 + tid] * v;
+        __syncwarp();
+      }
+    }
     __syncthreads();
   }
 }

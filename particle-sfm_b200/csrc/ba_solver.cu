@@ -732,7 +732,7 @@ void ensure_pairs(psfm_ba_solver* S) {
   S->d_chunk_beg.alloc((size_t)S->nchunks + 1, st); S->d_chunk_beg.upload(chunk_beg.data(), (size_t)S->nchunks + 1, st);
   S->d_W.alloc(18 * (size_t)M, st); S->d_WH.alloc(18 * (size_t)M, st);
   S->d_xcam.alloc((size_t)F * NVX, st); S->d_xcamrep.alloc((size_t)NREP * F * NVX, st); S->d_xcamrep.zero(st);
-  S->d_Sblk.alloc((size_t)nb * 36, st); S->d_S.alloc((size_t)S->NS * S->NS, st); S->d_cholfail.alloc(1, st);
+  S->d_Sblk.alloc((size_t)nb * 36, st); S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), st); S->d_cholfail.alloc(1, st);
   PSFM_CUDA(cudaStreamSynchronize(st));
   S->pairs_ready = true;
   tm.mark("pair structure (explicit Schur)");
@@ -759,7 +759,8 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   a.lin_cam = S->d_lin.p; a.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
   a.prep_intr = S->d_prep.p + (size_t)S->F * NVL; a.xcam = S->d_xcam.p;
   a.scale_c = S->d_scale_c.p; a.Dc2 = S->d_Dc2.p; a.active = S->d_active.p;
-  a.F = S->F; a.C = S->C; a.NS = S->NS; a.S = S->d_S.p;
+  a.rhs = S->d_rhs.p;
+  a.F = S->F; a.C = S->C; a.NS = S->NS; a.lda = S->NS + 1; a.S = S->d_S.p;
   if (S->nblocks) { k_schur_assemble_blocks<<<grid_for((size_t)S->nblocks * 36), 256, 0, st>>>(a); PSFM_LAUNCH_CHECK(); }
   k_schur_assemble_local<<<grid_for(S->F, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   dist::allreduce_sum(S->d_S.p, S->d_S.n, st);
@@ -768,8 +769,21 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   const int nbnd = 6 * S->F;
   int bw = std::min(S->bw, nbnd);
   if (dist::world_size() > 1) bw = nbnd;   // ranks may see different spans: use the dense band
-  k_chol_banded<<<1, 1024, 0, st>>>(S->d_S.p, S->NS, nbnd, bw, S->d_rhs.p, S->d_x.p, S->d_cholfail.p);
-  PSFM_LAUNCH_CHECK();
+  {
+    static int grid_limit = 0;
+    if (grid_limit == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      PSFM_CUDA(cudaGetDevice(&dev));
+      PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_blocked, 256, 0));
+      grid_limit = std::max(1, sms * std::min(per_sm, 1));
+    }
+    CholArgs ca;
+    ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
+    void* kargs[] = {(void*)&ca};
+    PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid_limit), dim3(256), kargs, 0, st));
+    PSFM_LAUNCH_CHECK();
+  }
   int fail = 0;
   PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   PSFM_CUDA(cudaStreamSynchronize(st));
