@@ -148,7 +148,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=WORKLOAD["num_points"], help="trajectories of the BA workload")
     ap.add_argument("--cpu-points", type=int, default=CPU_SAMPLE_POINTS)
-    ap.add_argument("--solver", default="iterative", choices=["iterative", "exact"])
+    ap.add_argument("--solver", default="auto", choices=["auto", "iterative", "exact"],
+                    help="auto = the reference rule (bundle_adjustment.cc:276-286): exact Schur for <= 1000 images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-traj", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -196,7 +197,8 @@ def main():
     full, truth = syn.make_ba_problem(**w)
     M_total = full.num_observations
     prob = full.shard(rank, world)
-    solver_mode = _abi.SOLVER_ITERATIVE_SCHUR if args.solver == "iterative" else _abi.SOLVER_EXACT_SCHUR
+    solver_mode = {"auto": _abi.SOLVER_AUTO, "iterative": _abi.SOLVER_ITERATIVE_SCHUR,
+                   "exact": _abi.SOLVER_EXACT_SCHUR}[args.solver]
     o = global_pass_b_options(_abi, lib, solver_mode)
     init = (full.qvec.copy(), full.tvec.copy(), full.xyz.copy(), full.cam_params.copy())
 
@@ -230,24 +232,49 @@ def main():
     ate = syn.umeyama_ate(syn.camera_centres(prob.qvec, prob.tvec), truth["centres"])
 
     # ---------------- roofline of the dominant kernel (live CUDA events) ----------------
+    # Algorithmic bytes per launch (factored-Jacobian formulation):
+    #   Jacobian sweep      read xy 16 + idx 4, write D 24 + r 16; per point X 24 r, E'E/E'r 72 w
+    #   implicit S*p        read D 24 + idx 4; per point X 24 + H~ 48
+    #   W / W H~            read D 24 + idx 4, write 288; per point 120
+    #   pair products       every W and W H~ row once (288 B/obs) + 8 B/pair entry
     peak, peak_src = read_peaks()
     M_local = prob.num_observations
     L = w["track_len"]
-    sp_bytes = (96 + 48 + 16 + 8 + 48.0 / L) * M_local          # implicit S*p, SURVEY.md §8d (+16 B focal column)
-    lin_bytes = (24 + 176 + 96.0 / L) * M_local                 # Jacobian sweep, pass B
-    n_sp = sum(s.num_schur_products for s in summaries)
-    n_lin = sum(s.num_linearize for s in summaries)
-    sp_ms = sum(s.schur_product_ms for s in summaries) / max(n_sp, 1)
-    lin_ms = sum(s.linearize_ms for s in summaries) / max(n_lin, 1)
-    sp_gbs = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
-    lin_gbs = lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
-    roofline = {"kernel": "k_schur_product (implicit S*p, one per PCG iteration)", "bound": "hbm", "achieved": sp_gbs,
-                "peak": peak, "unit": "GB/s", "frac": sp_gbs / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": sp_bytes, "avg_launch_ms": sp_ms, "launches": n_sp,
-                "share_of_step": sum(s.schur_product_ms for s in summaries) / (1e3 * t_local)}
-    roofline_lin = {"kernel": "k_linearize (Jacobian sweep)", "bound": "hbm", "achieved": lin_gbs, "peak": peak,
-                    "unit": "GB/s", "frac": lin_gbs / peak, "traffic": None,
-                    "algorithmic_bytes_per_launch": lin_bytes, "avg_launch_ms": lin_ms, "launches": n_lin}
+    pairs_local = M_local * (L + 1) / 2.0
+    kernels = {
+        "k_linearize (Jacobian sweep)": dict(ms=sum(s.linearize_ms for s in summaries), n=sum(s.num_linearize for s in summaries),
+                                             bytes=(20 + 40 + 96.0 / L) * M_local),
+        "k_schur_product (implicit S*p, one per PCG iteration)": dict(ms=sum(s.schur_product_ms for s in summaries),
+                                                                      n=sum(s.num_schur_products for s in summaries),
+                                                                      bytes=(28 + 72.0 / L) * M_local),
+        "k_schur_w (W = Jc'Jp and W H~ per observation)": dict(ms=sum(s.schur_w_ms for s in summaries),
+                                                              n=sum(s.num_explicit_solves for s in summaries),
+                                                              bytes=(28 + 288 + 120.0 / L) * M_local),
+        "k_schur_pairs (image-pair blocks of the Schur complement)": dict(ms=sum(s.schur_pairs_ms for s in summaries),
+                                                                         n=sum(s.num_explicit_solves for s in summaries),
+                                                                         bytes=288.0 * M_local + 8.0 * pairs_local),
+        "k_schur_assemble + k_chol_blocked (reduced system solve)": dict(ms=sum(s.cholesky_ms for s in summaries),
+                                                                        n=sum(s.num_explicit_solves for s in summaries), bytes=None),
+    }
+
+    def roof(name):
+        k = kernels[name]
+        if k["n"] == 0 or k["ms"] <= 0:
+            return None
+        avg = k["ms"] / k["n"]
+        d = {"kernel": name, "bound": "hbm", "avg_launch_ms": avg, "launches": k["n"], "share_of_step": k["ms"] / (1e3 * t_local),
+             "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None}
+        if k["bytes"]:
+            d["algorithmic_bytes_per_launch"] = k["bytes"]
+            d["achieved"] = k["bytes"] / (avg * 1e-3) / 1e9
+            d["frac"] = d["achieved"] / peak
+        else:
+            d["achieved"], d["frac"] = None, None
+        return d
+    ranked = sorted((n for n in kernels if kernels[n]["bytes"] and kernels[n]["n"]), key=lambda n: -kernels[n]["ms"])
+    roofline = roof(ranked[0])
+    roofline_lin = roof("k_linearize (Jacobian sweep)")
+    roofline_all = [r for r in (roof(n) for n in kernels) if r]
     S.close()
 
     # ---------------- end to end through the C ABI on host buffers ----------------
@@ -273,10 +300,11 @@ def main():
         "config": {"workload": f"global BA pass B (rotation+translation+focal+points), F={w['num_images']} frames x "
                                f"P={w['num_points']} trajectories x L={L} obs/track, M={M_total} observations, seed {w['seed']}",
                    "options": "GlobalBundleAdjustment (SoftL1, f_tol 1e-6, g_tol 1, p_tol 1e-8, <=50 LM its)",
-                   "linear_solver": "PCG on the reduced camera system, Schur-Jacobi, eta=0.1, <=100 its (Ceres ITERATIVE_SCHUR semantics)"
-                   if args.solver == "iterative" else "PCG to |r|<=1e-10|b| (exact-step mode)",
-                   "parallelism": f"points sharded over {world} GPU(s), one NCCL all-reduce per PCG step",
-                   "l2": "working set (J = 1.1 GB/6M obs) is larger than the 126 MB L2; no flush needed"},
+                   "linear_solver": {2: "PCG on the reduced camera system, Schur-Jacobi, eta=0.1, <=100 its (Ceres ITERATIVE_SCHUR semantics)",
+                                     1: "exact step: explicit Schur complement + banded Cholesky on the device (reference rule for <= 1000 images)"}
+                   [s_last.linear_solver_used],
+                   "parallelism": f"points sharded over {world} GPU(s); NCCL all-reduce of the camera-side accumulators / reduced system",
+                   "l2": "per-step working set (observations + W arrays, > 2 GB) is larger than the 126 MB L2; no flush needed"},
         "lm_iterations_per_step": iters, "pcg_iterations_per_step": lin_its,
         "obs_iterations_per_sec": M_total * sum(s.num_iterations for s in summaries) / t_total,
         "device_ms_per_step": sum(s.device_ms for s in summaries) / len(summaries),
@@ -286,7 +314,7 @@ def main():
                 "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": roofline, "roofline_linearize": roofline_lin,
+        "roofline": roofline, "roofline_linearize": roofline_lin, "roofline_all_kernels": roofline_all,
     }
 
     # ---------------- HP1: trajectory optimiser, pts/s (rank 0, N = 1 shape) ----------------

@@ -132,9 +132,10 @@ typedef enum {
   /* The reference rule (bundle_adjustment.cc:276-286): <=1000 images -> exact Schur
      step (DENSE_/SPARSE_SCHUR), otherwise ITERATIVE_SCHUR + SCHUR_JACOBI. */
   PSFM_BA_SOLVER_AUTO = 0,
-  /* Exact Gauss-Newton/LM step: PCG on the reduced camera system driven to
-     `exact_r_tolerance` (the GPU never factorises; the step equals the Cholesky step
-     of DENSE_/SPARSE_SCHUR to ~1e-10). */
+  /* Exact Gauss-Newton/LM step, as DENSE_/SPARSE_SCHUR: the reduced camera system is
+     formed explicitly on the device and factorised (banded Cholesky).  When that is not
+     possible (principal point refined, or > 4 GB of reduced system) the same PCG is driven
+     to `exact_r_tolerance` instead. */
   PSFM_BA_SOLVER_EXACT_SCHUR = 1,
   /* Ceres ITERATIVE_SCHUR + SCHUR_JACOBI semantics: eta forcing, x0 = 0,
      max_linear_solver_iterations. The throughput mode. */
@@ -222,6 +223,11 @@ typedef struct {
   int32_t num_schur_products;        /* applications of S*p */
   int32_t linear_solver_used;        /* psfm_ba_linear_solver actually used */
   int32_t world_size;
+  /* explicit (exact) reduced-system path, summed CUDA-event times */
+  int32_t num_explicit_solves;
+  double schur_w_ms;                 /* per-observation W, W H~ */
+  double schur_pairs_ms;             /* image-pair block products */
+  double cholesky_ms;                /* assembly + blocked Cholesky + triangular solves */
 } psfm_ba_summary;
 
 void psfm_ba_default_options(psfm_ba_options* o);          /* bundle_adjustment.h defaults */

@@ -132,6 +132,10 @@ class BASummary(C.Structure):
         ("num_schur_products", C.c_int32),
         ("linear_solver_used", C.c_int32),
         ("world_size", C.c_int32),
+        ("num_explicit_solves", C.c_int32),
+        ("schur_w_ms", C.c_double),
+        ("schur_pairs_ms", C.c_double),
+        ("cholesky_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -99,7 +99,7 @@ struct psfm_ba_solver {
   HostScalars* hs = nullptr;
   cudaStream_t stream = nullptr;
   EventPool events;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lin, ev_sp;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lin, ev_sp, ev_sw, ev_pairs, ev_chol;
 
   TileCtx tc() const {
     TileCtx t;
@@ -746,13 +746,23 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   w.L = lin_of(S); w.pose16 = S->d_pose16.p; w.X = S->d_X[S->cur].p; w.ht = S->d_hinv.p; w.wk = S->d_wk.p;
   w.K = S->d_K[S->cur].p; w.W = S->d_W.p; w.WH = S->d_WH.p; w.acc_cam = S->d_xcamrep.p;
   w.rep_stride = (size_t)S->F * NVX; w.intr = c.intr;
+  auto mark = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, bool begin) {
+    cudaEvent_t e = S->events.get();
+    PSFM_CUDA(cudaEventRecord(e, st));
+    if (begin) v.push_back({e, nullptr}); else v.back().second = e;
+  };
+  mark(S->ev_sw, true);
   PSFM_TILE_LAUNCH(k_schur_w, NVX, 12, S, c.rot, w);
+  mark(S->ev_sw, false);
   fold_replicas(S, S->d_xcam.p, S->d_xcamrep.p, (size_t)S->F * NVX, nullptr, nullptr);
   S->d_Sblk.zero(st);
   PairArgs pa;
   pa.entries = S->d_entries.p; pa.chunk_blk = S->d_chunk_blk.p; pa.chunk_beg = S->d_chunk_beg.p;
   pa.W = S->d_W.p; pa.WH = S->d_WH.p; pa.Sblk = S->d_Sblk.p;
+  mark(S->ev_pairs, true);
   if (S->nchunks) { k_schur_pairs<<<S->nchunks, 128, 0, st>>>(pa); PSFM_LAUNCH_CHECK(); }
+  mark(S->ev_pairs, false);
+  mark(S->ev_chol, true);
   S->d_S.zero(st);
   AsmArgs a;
   a.Sblk = S->d_Sblk.p; a.blk_key = S->d_blk_key.p; a.nblocks = S->nblocks;
@@ -784,6 +794,7 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
     PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid_limit), dim3(256), kargs, 0, st));
     PSFM_LAUNCH_CHECK();
   }
+  mark(S->ev_chol, false);
   int fail = 0;
   PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   PSFM_CUDA(cudaStreamSynchronize(st));
@@ -903,7 +914,7 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
     return PSFM_ZERO_RESIDUALS;
   }
   const double t0 = now_s();
-  S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
+  S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
   upload_state(S);
   set_masks_and_unit_scale(S, c);
   s.num_residuals_reduced = 2 * M_all;
@@ -981,6 +992,10 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
   s.device_ms = ms;
   for (auto& e : S->ev_lin) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.linearize_ms += ms; }
   for (auto& e : S->ev_sp) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_product_ms += ms; }
+  for (auto& e : S->ev_sw) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_w_ms += ms; }
+  for (auto& e : S->ev_pairs) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_pairs_ms += ms; }
+  for (auto& e : S->ev_chol) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.cholesky_ms += ms; }
+  s.num_explicit_solves = (int)S->ev_pairs.size();
   s.num_linearize = (int)S->ev_lin.size();
   s.num_schur_products = (int)S->ev_sp.size();
   s.num_iterations = iteration;
@@ -1179,7 +1194,7 @@ extern "C" int psfm_ba_linear_step(psfm_ba_solver* S, const psfm_ba_options* opt
     RunCfg c;
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
-      S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear();
+      S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
     upload_state(S);
     set_masks_and_unit_scale(S, c);
     linearize_and_measure(S, c, radius, false, true);
