@@ -155,3 +155,50 @@ def test_zero_residuals_and_errors(gpu):
     bad.obs_image = bad.obs_image.copy(); bad.obs_image[0] = 99
     st = bad.struct()
     assert _lib.lib().psfm_ba_solve(C.byref(st), C.byref(o), C.byref(s)) == _abi.PSFM_ERR_INVALID
+
+
+def test_exact_mode_long_tracks_dense_reduced_system(gpu):
+    """Tracks spanning (almost) the whole sequence make the reduced camera system dense
+    (Sintel-like: ~50 frames, tracks of 3..50 frames): the band-aware Cholesky must take the
+    dense route and still match the oracle's dense Cholesky path."""
+    prob, truth = syn.make_ba_problem(50, 3000, 12, seed=14, track_len_range=(3, 50))
+    o = _opts(True, True, _abi.SOLVER_AUTO)          # <= 1000 images -> exact Schur
+    p0, p1 = prob.copy(), prob.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert s1.linear_solver_used == _abi.SOLVER_EXACT_SCHUR and s1.num_explicit_solves == s1.num_iterations
+    assert s1.num_iterations == s0.num_iterations and s1.termination == s0.termination
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-8 * s0.final_cost
+    for a, b in ((p1.qvec, p0.qvec), (p1.tvec, p0.tvec), (p1.xyz, p0.xyz), (p1.cam_params, p0.cam_params)):
+        assert _rel(a, b) < 1e-7
+
+
+def test_exact_mode_duplicate_observations_and_dynamic_dropouts(gpu):
+    """A point observed twice in the same image (both orders enter the diagonal block) and
+    tracks with holes (30 % of the observations dropped, as after motion segmentation)."""
+    prob, _ = syn.make_ba_problem(30, 2500, 10, seed=15, dynamic_fraction=0.3)
+    rng = np.random.default_rng(0)
+    dup = rng.choice(prob.num_observations, 200, replace=False)
+    xy = np.concatenate([prob.obs_xy, prob.obs_xy[dup] + rng.normal(0, 0.3, (200, 2))])
+    p = _abi.BAProblem(prob.qvec, prob.tvec, prob.xyz, prob.cam_params, np.concatenate([prob.obs_image, prob.obs_image[dup]]),
+                       np.concatenate([prob.obs_point, prob.obs_point[dup]]), xy, prob.image_camera,
+                       prob.pose_constant, prob.tvec_constant_mask, prob.camera_constant)
+    for rot, focal in ((True, True), (False, False)):
+        o = _opts(rot, focal, _abi.SOLVER_EXACT_SCHUR)
+        p0, p1 = p.copy(), p.copy()
+        s0 = oracle.ba_solve(p0, o)
+        s1 = ba.solve_problem(p1, o)
+        assert s1.num_iterations == s0.num_iterations
+        assert abs(s1.final_cost - s0.final_cost) <= 1e-8 * s0.final_cost
+        assert _rel(p1.xyz, p0.xyz) < 1e-6 and _rel(p1.tvec, p0.tvec) < 1e-6
+
+
+def test_exact_mode_principal_point_falls_back_to_tight_pcg(gpu):
+    prob, _ = syn.make_ba_problem(10, 600, 6, seed=16)
+    o = _opts(True, True, _abi.SOLVER_EXACT_SCHUR, pp=True)
+    p0, p1 = prob.copy(), prob.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert s1.num_explicit_solves == 0 and s1.num_schur_products > 0
+    assert s1.num_iterations == s0.num_iterations
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-6 * s0.final_cost
