@@ -401,48 +401,56 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
   __syncthreads();
   for (int c0 = 0; c0 < ns; c0 += CB) {
     const int w = min(CB, ns - c0), c1 = c0 + w;
-    // ---- (1) diagonal block, redundantly per CTA
-    for (int t = tid; t < CB * CB; t += 256) {
-      const int r = t / CB, c = t % CB;
-      sD[r][c] = (r < w && c <= r) ? A[(size_t)(c0 + r) * lda + c0 + c] : 0.0;
+    // ---- (1) diagonal block, redundantly per CTA: warp 0 factors it in registers
+    //      (lane r owns row r; padded to 32x32 with an identity tail when w < 32)
+    if (tid < CB) {
+      double arow[CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c)
+        arow[c] = (tid < w && c <= tid && c < w) ? A[(size_t)(c0 + tid) * lda + c0 + c] : ((c == tid && tid >= w) ? 1.0 : 0.0);
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const double d = __shfl_sync(0xffffffffu, arow[j], j);
+        if (!(d > 0.0) || isinf(d)) bad = true;
+        const double dj = sqrt(d);
+        if (tid == j) arow[j] = dj;
+        else if (tid > j) arow[j] = arow[j] / dj;
+        const double lr = arow[j];
+#pragma unroll
+        for (int c = j + 1; c < CB; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, lr, c);
+          if (tid >= c) arow[c] -= lr * lc;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CB; ++c) sD[tid][c] = arow[c];
+      if (bad && tid == 0) s_bad = 1;
     }
     __syncthreads();
-    for (int j = 0; j < w; ++j) {
-      if (tid == 0) {
-        const double d = sD[j][j];
-        if (!(d > 0.0) || isinf(d)) s_bad = 1;
-        sD[j][j] = sqrt(d);
-      }
-      __syncthreads();
-      if (s_bad) break;
-      const double dj = sD[j][j];
-      if (tid > j && tid < w) sD[tid][j] /= dj;
-      __syncthreads();
-      for (int t = tid; t < w * w; t += 256) {
-        const int r = t / w, c = t % w;
-        if (c > j && r >= c) sD[r][c] -= sD[r][j] * sD[c][j];
-      }
-      __syncthreads();
-    }
     if (s_bad) break;     // uniform across the grid: every CTA factors the same block
     // ---- rows below the panel that can be non-zero
     const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
     const int nband = max(0, rb - c1);
     const int arrow0 = max(a.nb, c1);
     const int npos = nband + (nrows - arrow0);
-    // ---- (2) solve X L11' = A21 for these rows (one thread per row)
-    for (int q = blockIdx.x * CB; q < npos; q += gridDim.x * CB) {
+    // ---- (2) solve X L11' = A21 for these rows (one thread per row, registers)
+    for (int q = blockIdx.x * 256; q < npos; q += gridDim.x * 256) {
       const int pos = q + tid;
-      if (tid < CB && pos < npos) {
+      if (pos < npos) {
         double* row = A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0;
         double xr[CB];
-#pragma unroll 4
-        for (int k = 0; k < w; ++k) {
-          double s = row[k];
-          for (int m = 0; m < k; ++m) s -= xr[m] * sD[k][m];
-          xr[k] = s / sD[k][k];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) xr[k] = (k < w) ? row[k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+          double sacc_ = xr[k];
+#pragma unroll
+          for (int m = 0; m < k; ++m) sacc_ -= xr[m] * sD[k][m];
+          xr[k] = sacc_ / sD[k][k];
         }
-        for (int k = 0; k < w; ++k) row[k] = xr[k];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) if (k < w) row[k] = xr[k];
       }
     }
     __threadfence();

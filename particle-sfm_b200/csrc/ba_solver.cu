@@ -674,6 +674,15 @@ void ensure_pairs(psfm_ba_solver* S) {
     PSFM_CUDA(cudaMemcpyAsync(&h_span, span.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSFM_CUDA(cudaStreamSynchronize(st));
     S->npairs = total;
+    if (dist::world_size() > 1) {   // every rank must use the same band: max span over all shards
+      DBuf<double> sp; sp.alloc(1, st);
+      k_fill<<<1, 32, 0, st>>>(sp.p, (double)h_span, 1); PSFM_LAUNCH_CHECK();
+      dist::allreduce_max(sp.p, 1, st);
+      double hs = 0.0;
+      PSFM_CUDA(cudaMemcpyAsync(&hs, sp.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      PSFM_CUDA(cudaStreamSynchronize(st));
+      h_span = (int)(hs + 0.5);
+    }
     S->bw = 6 * h_span + 5;
   }
   if (S->npairs >= (1ll << 31)) { set_error("too many observation pairs for the explicit Schur complement"); throw CudaFail{PSFM_ERR_UNSUPPORTED}; }
@@ -777,8 +786,7 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   const int nbnd = 6 * S->F;
-  int bw = std::min(S->bw, nbnd);
-  if (dist::world_size() > 1) bw = nbnd;   // ranks may see different spans: use the dense band
+  const int bw = std::min(S->bw, nbnd);
   {
     static int grid_limit = 0;
     if (grid_limit == 0) {
@@ -791,7 +799,10 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
     CholArgs ca;
     ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
     void* kargs[] = {(void*)&ca};
-    PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid_limit), dim3(256), kargs, 0, st));
+    // few CTAs when the band is narrow (cheaper grid barriers), all SMs for a dense system
+    const int tiles = (std::min(bw + 2, nbnd) + (S->NS + 1 - nbnd) + CB - 1) / CB;
+    const int grid = std::max(1, std::min(grid_limit, tiles * (tiles + 1) / 2));
+    PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid), dim3(256), kargs, 0, st));
     PSFM_LAUNCH_CHECK();
   }
   mark(S->ev_chol, false);
