@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSFM_ABI_VERSION 1
+#define PSFM_ABI_VERSION 2
 
 typedef enum {
   PSFM_OK = 0,
@@ -228,6 +228,10 @@ typedef struct {
   double schur_w_ms;                 /* per-observation W, W H~ */
   double schur_pairs_ms;             /* image-pair block products */
   double cholesky_ms;                /* assembly + blocked Cholesky + triangular solves */
+  /* fused tile path (k_schur_tile): schur_w_ms is its time, schur_pairs_ms stays 0 */
+  int64_t num_pair_entries;          /* observation pairs of the Schur complement on this rank */
+  int32_t num_pair_tasks;            /* (tile, image pair) runs of those entries */
+  int32_t explicit_fused;            /* 1: k_schur_tile, 0: k_schur_w + k_schur_pairs */
 } psfm_ba_summary;
 
 void psfm_ba_default_options(psfm_ba_options* o);          /* bundle_adjustment.h defaults */

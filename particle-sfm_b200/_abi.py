@@ -136,6 +136,9 @@ class BASummary(C.Structure):
         ("schur_w_ms", C.c_double),
         ("schur_pairs_ms", C.c_double),
         ("cholesky_ms", C.c_double),
+        ("num_pair_entries", C.c_int64),
+        ("num_pair_tasks", C.c_int32),
+        ("explicit_fused", C.c_int32),
     ]
 
     def as_dict(self):

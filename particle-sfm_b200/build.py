@@ -31,7 +31,7 @@ UNITS = [
     ("ba_solver.cu", []),
     ("traj_solver.cu", ["-fmad=false"]),
 ]
-HEADERS = ["psfm_common.cuh", "ba_kernels.cuh", "ba_small_kernels.cuh", "dist.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
 
 
 def _stale(target, deps):

@@ -97,7 +97,7 @@ __device__ __forceinline__ void loss_eval(const LossP l, const double s, double&
 //   sred [9*32]          block-reduction scratch
 //   simg [12][cap_ns]    per image segment: R (row-major 9), t (3)
 //   sx   [6][cap_ns]     per image segment: scaled input vector (rot 3 | t 3)
-//   spt  [NPT][cap_np]   per point: X (3) [, H~ (6) [, w^ (3)]]
+//   spt  [NPT][cap_np]   per point: X (3) [, H~ (6) [, w^ or G'E focal row (3) [, w^ (3)]]]
 template <int TILE>
 struct TileSmem {
   double *sv, *sw, *sred, *simg, *sx, *spt;
@@ -148,7 +148,8 @@ template <int TILE>
 __device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE>& sm, const TileInfo& ti,
                                                const double* __restrict__ pose16, const double* __restrict__ xs,
                                                const double* __restrict__ X, const double* __restrict__ p6,
-                                               const double* __restrict__ p3, bool need_cam) {
+                                               const double* __restrict__ p3, bool need_cam,
+                                               const double* __restrict__ p3b = nullptr) {
   const int tid = threadIdx.x;
   const int cns = sm.cap_ns, cnp = sm.cap_np;
   for (int j = tid; j <= ti.np; j += TILE) sm.pstart[j] = __ldg(tc.pt_ptr + ti.pt0 + j) - ti.base;
@@ -186,6 +187,12 @@ __device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE>
     for (int j = tid; j < ti.np * 3; j += TILE) {
       const int k = j / ti.np, l = j - k * ti.np;
       sm.spt[(9 + k) * cnp + l] = __ldg(p3 + (size_t)k * tc.P + ti.pt0 + l);
+    }
+  }
+  if (p3b) {
+    for (int j = tid; j < ti.np * 3; j += TILE) {
+      const int k = j / ti.np, l = j - k * ti.np;
+      sm.spt[(12 + k) * cnp + l] = __ldg(p3b + (size_t)k * tc.P + ti.pt0 + l);
     }
   }
   __syncthreads();

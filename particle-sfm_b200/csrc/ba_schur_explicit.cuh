@@ -210,6 +210,239 @@ __global__ void __launch_bounds__(128) k_schur_pairs(const PairArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ fused tile path: W in shared memory, pairs per tile
+//
+// A point never straddles a tile, so every (i, j) observation pair of the Schur complement
+// lives inside one tile.  k_schur_tile keeps W_i and W_i H~ of its <= TILE observations in
+// shared memory (nothing per-observation goes to HBM) and runs the tile's pair TASKS: a task
+// is the run of pair entries of one image pair (a, b) inside the tile; two threads share a
+// task (block rows 0-2 / 3-5), accumulate sum (W_i H~) W_j' in registers and issue one RED
+// per element into the band-block accumulator  Sband[a][b - a][36]  (b - a <= span, the
+// longest image span of a track, global over the ranks).  The per-image sums (rot-t cross
+// block, focal column, rhs correction -W w^) are reduced per image segment as in the other
+// tile kernels.
+
+constexpr int NVX2 = 27;   // NVX (21) | -(W w^) rot (3) | t (3)
+constexpr int WW = 37;     // shared-memory stride of one observation's [W (18) | W H~ (18)] (+1 pad)
+
+struct StArgs {
+  Lin L;
+  const double* pose16;
+  const double* X;
+  const double* ht;     // [6][P]
+  const double* wt;     // [3][P] w^ = H~ g^
+  const double* wk;     // [9][P] G'E per point (focal row used)
+  const double* K;
+  double* acc_cam;      // [NREP][F][NVX2]
+  size_t rep_stride;
+  int intr;
+  const unsigned int* entries;   // (li << 16) | lj, tile-local indices, sorted by (tile, a, b)
+  const int* task_slot;          // [ntasks] band-block slot a * (span + 1) + (b - a)
+  const int* task_beg;           // [ntasks + 1] entry range of the task
+  const int* tile_task;          // [T + 1] task range of the tile
+  double* Sband;                 // [nrep][F * (span + 1) * 36]
+  size_t band_stride;
+  int nrep_mask;
+};
+
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(const TileCtx tc, const StArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, WW, 15, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
+  const int tid = threadIdx.x;
+  const bool act = tid < ti.n;
+  const size_t M = tc.M;
+  const size_t i = (size_t)ti.base + tid;
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0;
+  if (act) {
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
+  }
+  const int t0 = __ldg(a.tile_task + blockIdx.x), nt = __ldg(a.tile_task + blockIdx.x + 1) - t0;
+  const double inv_f = (a.intr >= 1) ? 1.0 / __ldg(a.K) : 0.0;
+  // per point: X (0..2), H~ (3..8), focal row of G'E (9..11), w^ (12..14)
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wk, true, a.wt);
+  double* sv = sm.sv + tid;
+#pragma unroll
+  for (int k = 0; k < NVX2; ++k) sv[k * TILE] = 0.0;
+  double W[6][3], WH[6][3];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { W[r][k] = 0.0; WH[r][k] = 0.0; }
+  if (act) {
+    ObsGeom g;
+    load_geom<TILE>(sm, ls, lp, g);
+    const int cnp = sm.cap_np;
+    double hv[6], wkp[3], wh[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { wkp[k] = sm.spt[(9 + k) * cnp + lp]; wh[k] = sm.spt[(12 + k) * cnp + lp]; }
+    double jp[2][3], jc[2][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      jp[0][k] = a00 * g.R[k] + a02 * g.R[6 + k];
+      jp[1][k] = a00 * g.R[3 + k] + a12 * g.R[6 + k];
+    }
+    if (ROT) {
+      jc[0][0] = 2.0 * a02 * g.w[1]; jc[0][1] = 2.0 * (a00 * g.w[2] - a02 * g.w[0]); jc[0][2] = -2.0 * a00 * g.w[1];
+      jc[1][0] = 2.0 * (a12 * g.w[1] - a00 * g.w[2]); jc[1][1] = -2.0 * a12 * g.w[0]; jc[1][2] = 2.0 * a00 * g.w[0];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { jc[0][k] = 0.0; jc[1][k] = 0.0; }
+    }
+    jc[0][3] = a00; jc[0][4] = 0.0; jc[0][5] = a02;
+    jc[1][3] = 0.0; jc[1][4] = a00; jc[1][5] = a12;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) W[r][k] = jc[0][r] * jp[0][k] + jc[1][r] * jp[1][k];
+      WH[r][0] = W[r][0] * hv[0] + W[r][1] * hv[1] + W[r][2] * hv[2];
+      WH[r][1] = W[r][0] * hv[1] + W[r][1] * hv[3] + W[r][2] * hv[4];
+      WH[r][2] = W[r][0] * hv[2] + W[r][1] * hv[4] + W[r][2] * hv[5];
+    }
+    if (ROT) {   // rot-t cross block of F'F: (Jr' Jt)[r][c]
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * TILE] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
+    }
+    if (a.intr >= 1) {
+      const double zf = (g.w[2] + g.tz) * inv_f;
+      const double jf0 = -a02 * zf, jf1 = -a12 * zf;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        sv[(9 + r) * TILE] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
+        sv[(15 + r) * TILE] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
+      }
+    }
+#pragma unroll
+    for (int r = (ROT ? 0 : 3); r < 6; ++r) sv[(21 + r) * TILE] = -(W[r][0] * wh[0] + W[r][1] * wh[1] + W[r][2] * wh[2]);
+  }
+  __syncthreads();
+  {
+    double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
+    tile_reduce_images<TILE>(sm, ti, NVX2, [&](int k, int img, double acc) {
+      if (acc != 0.0) atomicAdd(dst + (size_t)img * NVX2 + k, acc);
+    });
+  }
+  __syncthreads();
+  // the reduction rows are dead: the same shared memory now holds [W | W H~] per observation
+  double* sww = sm.sv;
+  if (act) {
+    double* o = sww + (size_t)tid * WW;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { o[3 * r + k] = W[r][k]; o[18 + 3 * r + k] = WH[r][k]; }
+  }
+  __syncthreads();
+  double* band = a.Sband + (size_t)(blockIdx.x & a.nrep_mask) * a.band_stride;
+  const int nq = ROT ? 2 * nt : nt;
+  for (int q = tid; q < nq; q += TILE) {
+    const int t = t0 + (ROT ? (q >> 1) : q), half = ROT ? (q & 1) : 1;
+    const int e0 = __ldg(a.task_beg + t), e1 = __ldg(a.task_beg + t + 1);
+    double acc[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+    for (int e = e0; e < e1; ++e) {
+      const unsigned int u = __ldg(a.entries + e);
+      const double* A = sww + (size_t)(u >> 16) * WW + 18 + 9 * half;
+      const double* B = sww + (size_t)(u & 0xffffu) * WW;
+      double av[9], bv[18];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) av[k] = A[k];
+#pragma unroll
+      for (int k = 0; k < 18; ++k) bv[k] = B[k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          acc[6 * r + c] += av[3 * r] * bv[3 * c] + av[3 * r + 1] * bv[3 * c + 1] + av[3 * r + 2] * bv[3 * c + 2];
+    }
+    double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * half;
+#pragma unroll
+    for (int k = 0; k < 18; ++k) atomicAdd(dst + k, acc[k]);
+  }
+}
+
+// ---- tile-local pair structure (built once per problem)
+
+// entries started by observation j (see k_pair_count); key = (tile, image a, image b), value =
+// the two tile-local observation indices
+__global__ void k_pair_fill_tile(const int* pt_ptr, const int* obs_pt, const int* obs_img, const int* ptr, int M,
+                                 const int* tile_start, int T, int fbits, unsigned long long* keys, unsigned int* vals) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  int lo = 0, hi = T;           // tile of j: last tile with tile_start <= j
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tile_start[mid] <= j) lo = mid; else hi = mid;
+  }
+  const int base = tile_start[lo];
+  const int p = obs_pt[j];
+  const int b = pt_ptr[p], e = pt_ptr[p + 1];
+  const unsigned long long a = (unsigned long long)obs_img[j];
+  const unsigned long long khi = ((unsigned long long)lo << (2 * fbits)) | (a << fbits);
+  size_t o = (size_t)ptr[j];
+  for (int k = j; k < e; ++k, ++o) {
+    keys[o] = khi | (unsigned long long)obs_img[k];
+    vals[o] = ((unsigned)(j - base) << 16) | (unsigned)(k - base);
+  }
+  for (int k = j - 1; k >= b && obs_img[k] == (int)a; --k, ++o) {
+    keys[o] = khi | a;
+    vals[o] = ((unsigned)(j - base) << 16) | (unsigned)(k - base);
+  }
+}
+
+// task t (one run of equal keys) -> band-block slot; tile -> first task (lower bound)
+__global__ void k_task_slots(const unsigned long long* ukeys, int ntasks, int fbits, int span, int* slot) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks) return;
+  const unsigned long long k = ukeys[t], mask = (1ull << fbits) - 1;
+  const int b = (int)(k & mask), a = (int)((k >> fbits) & mask);
+  slot[t] = a * (span + 1) + (b - a);
+}
+
+__global__ void k_tile_tasks(const unsigned long long* ukeys, int ntasks, int fbits, int T, int* tile_task) {
+  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile > T) return;
+  int lo = 0, hi = ntasks;      // first task whose tile >= this tile
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)(ukeys[mid] >> (2 * fbits)) < tile) lo = mid + 1; else hi = mid;
+  }
+  tile_task[tile] = lo;
+}
+
+// band blocks -> dense S:  S[6a+r][6b+c] -= s s' Sband[a][b-a][r][c]  (mirrored for a != b)
+struct BandAsmArgs {
+  const double* Sband;
+  const double* scale_c;
+  int F, span, lda;
+  double* S;
+};
+
+__global__ void k_schur_assemble_band(const BandAsmArgs a) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per_img = (size_t)(a.span + 1) * 36;
+  if (t >= (size_t)a.F * per_img) return;
+  const double x = a.Sband[t];
+  if (x == 0.0) return;
+  const int ia = (int)(t / per_img), rem = (int)(t % per_img), d = rem / 36, e = rem % 36, r = e / 6, c = e % 6;
+  const int ib = ia + d;
+  if (ib >= a.F) return;
+  const size_t row = 6 * (size_t)ia + r, col = 6 * (size_t)ib + c;
+  const double v = -a.scale_c[row] * a.scale_c[col] * x;
+  a.S[row * a.lda + col] += v;
+  if (d != 0) a.S[col * a.lda + row] += v;
+}
+
 // ------------------------------------------------------------------ assembly of the dense reduced system
 
 struct AsmArgs {
@@ -219,7 +452,8 @@ struct AsmArgs {
   const double* lin_cam;    // [F][NVL]  rot F'F (6) | t F'F (6) | ...
   const double* lin_intr;   // [C][NVI]
   const double* prep_intr;  // [C][NVI]
-  const double* xcam;       // [F][NVX]
+  const double* xcam;       // [F][xstride] per-image sums of k_schur_w (NVX) / k_schur_tile (NVX2)
+  int xstride;
   const double* scale_c;    // [NS]
   const double* Dc2;        // [NS]
   const unsigned char* active;
@@ -246,7 +480,7 @@ __global__ void k_schur_assemble_local(const AsmArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int NS = a.lda, F = a.F;
   if (j >= F) return;
-  const double* X = a.xcam + (size_t)j * NVX;
+  const double* X = a.xcam + (size_t)j * a.xstride;
   const size_t s0 = 6 * (size_t)j;
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
@@ -381,10 +615,60 @@ struct CholArgs {
   int ns, lda, nb, bw;
   double* x;      // [ns]
   int* fail;
+  unsigned long long* prof;   // optional [8]: SM cycles of CTA 0 per phase (PSFM_CHOL_PROFILE)
 };
 
 __device__ __forceinline__ int chol_row_of(int pos, int c1, int nband, int arrow0) {
   return pos < nband ? c1 + pos : arrow0 + (pos - nband);
+}
+
+// Warp-level Cholesky of one w x w (w <= 32) diagonal block at A (leading dimension lda):
+// lane r owns row r in registers, the block is padded to 32 x 32 with an identity tail.
+// Writes L to sD and 1/L[k][k] to sDinv; returns true on a non-positive pivot.
+__device__ __noinline__ bool chol_diag_warp(const double* __restrict__ A, int lda, int w,
+                                            double (*sD)[CB + 1], double* sDinv) {
+  const int lane = threadIdx.x & 31;
+  double arow[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c)
+    arow[c] = (lane < w && c <= lane) ? A[(size_t)lane * lda + c] : ((c == lane && lane >= w) ? 1.0 : 0.0);
+  bool bad = false;
+  double myinv = 1.0;
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
+    const double d = __shfl_sync(0xffffffffu, arow[j], j);
+    if (!(d > 0.0) || isinf(d)) bad = true;
+    const double idj = rsqrt(d);
+    if (lane == j) { arow[j] = d * idj; myinv = idj; }
+    else if (lane > j) arow[j] = arow[j] * idj;
+    const double lr = arow[j];
+#pragma unroll
+    for (int c = j + 1; c < CB; ++c) {
+      const double lc = __shfl_sync(0xffffffffu, lr, c);
+      if (lane >= c) arow[c] -= lr * lc;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CB; ++c) sD[lane][c] = arow[c];
+  sDinv[lane] = myinv;
+  return __any_sync(0xffffffffu, bad);
+}
+
+// One row x (w entries at row[0..w)) of the panel below the diagonal block: x L' = a, in
+// registers, right-looking so that the updates of one step are independent.
+__device__ __noinline__ void chol_row_solve(double* __restrict__ row, int w, const double (*sD)[CB + 1],
+                                            const double* sDinv) {
+  double xr[CB];
+#pragma unroll
+  for (int k = 0; k < CB; ++k) xr[k] = (k < w) ? row[k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < CB; ++k) {
+    xr[k] *= sDinv[k];
+#pragma unroll
+    for (int m = k + 1; m < CB; ++m) xr[m] -= xr[k] * sD[m][k];
+  }
+#pragma unroll
+  for (int k = 0; k < CB; ++k) if (k < w) row[k] = xr[k];
 }
 
 __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
@@ -393,41 +677,27 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
   __shared__ double sD[CB][CB + 1];
   __shared__ double sLi[CB][CB + 1];
   __shared__ double sLj[CB][CB + 1];
+  __shared__ double sDinv[CB];
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   const int ns = a.ns, lda = a.lda, nrows = a.ns + 1;     // rows incl. the rhs row
   double* A = a.A;
   if (tid == 0) s_bad = 0;
   __syncthreads();
+  const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  long long tk = prof ? clock64() : 0;
+#define PSFM_CHOL_TICK(slot)                                   \
+  if (prof) {                                                  \
+    const long long now_ = clock64();                          \
+    a.prof[slot] += (unsigned long long)(now_ - tk);           \
+    tk = now_;                                                 \
+  }
   for (int c0 = 0; c0 < ns; c0 += CB) {
     const int w = min(CB, ns - c0), c1 = c0 + w;
     // ---- (1) diagonal block, redundantly per CTA: warp 0 factors it in registers
-    //      (lane r owns row r; padded to 32x32 with an identity tail when w < 32)
-    if (tid < CB) {
-      double arow[CB];
-#pragma unroll
-      for (int c = 0; c < CB; ++c)
-        arow[c] = (tid < w && c <= tid && c < w) ? A[(size_t)(c0 + tid) * lda + c0 + c] : ((c == tid && tid >= w) ? 1.0 : 0.0);
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < CB; ++j) {
-        const double d = __shfl_sync(0xffffffffu, arow[j], j);
-        if (!(d > 0.0) || isinf(d)) bad = true;
-        const double dj = sqrt(d);
-        if (tid == j) arow[j] = dj;
-        else if (tid > j) arow[j] = arow[j] / dj;
-        const double lr = arow[j];
-#pragma unroll
-        for (int c = j + 1; c < CB; ++c) {
-          const double lc = __shfl_sync(0xffffffffu, lr, c);
-          if (tid >= c) arow[c] -= lr * lc;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < CB; ++c) sD[tid][c] = arow[c];
-      if (bad && tid == 0) s_bad = 1;
-    }
+    if (tid < CB && chol_diag_warp(A + (size_t)c0 * lda + c0, lda, w, sD, sDinv)) s_bad = 1;
     __syncthreads();
+    PSFM_CHOL_TICK(0);
     if (s_bad) break;     // uniform across the grid: every CTA factors the same block
     // ---- rows below the panel that can be non-zero
     const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
@@ -437,24 +707,12 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
     // ---- (2) solve X L11' = A21 for these rows (one thread per row, registers)
     for (int q = blockIdx.x * 256; q < npos; q += gridDim.x * 256) {
       const int pos = q + tid;
-      if (pos < npos) {
-        double* row = A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0;
-        double xr[CB];
-#pragma unroll
-        for (int k = 0; k < CB; ++k) xr[k] = (k < w) ? row[k] : 0.0;
-#pragma unroll
-        for (int k = 0; k < CB; ++k) {
-          double sacc_ = xr[k];
-#pragma unroll
-          for (int m = 0; m < k; ++m) sacc_ -= xr[m] * sD[k][m];
-          xr[k] = sacc_ / sD[k][k];
-        }
-#pragma unroll
-        for (int k = 0; k < CB; ++k) if (k < w) row[k] = xr[k];
-      }
+      if (pos < npos) chol_row_solve(A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0, w, sD, sDinv);
     }
+    PSFM_CHOL_TICK(1);
     __threadfence();
     grid.sync();
+    PSFM_CHOL_TICK(2);
     // every CTA has finished reading the unfactored diagonal block: CTA 0 stores L11
     if (blockIdx.x == 0)
       for (int t = tid; t < w * w; t += 256) {
@@ -470,6 +728,22 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
       while (ti * (ti + 1) / 2 > pr) --ti;
       const int tj = pr - ti * (ti + 1) / 2;
       __syncthreads();
+      double* dst[4];
+      double old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {          // this thread's four outputs: issue the loads early
+        const int r = (tid + 256 * u) / CB, c = (tid + 256 * u) % CB;
+        const int pi = ti * CB + r, pj = tj * CB + c;
+        dst[u] = nullptr;
+        old[u] = 0.0;
+        if (pi < npos && pj < npos && pj <= pi) {
+          const int gi = chol_row_of(pi, c1, nband, arrow0), gj = chol_row_of(pj, c1, nband, arrow0);
+          if (gj < ns) {       // the rhs row has no column
+            dst[u] = A + (size_t)gi * lda + gj;
+            old[u] = *dst[u];
+          }
+        }
+      }
       for (int t = tid; t < CB * CB; t += 256) {
         const int r = t / CB, c = t % CB;
         const int pi = ti * CB + r, pj = tj * CB + r;
@@ -477,22 +751,21 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
         sLj[r][c] = (pj < npos && c < w) ? A[(size_t)chol_row_of(pj, c1, nband, arrow0) * lda + c0 + c] : 0.0;
       }
       __syncthreads();
-      for (int t = tid; t < CB * CB; t += 256) {
-        const int r = t / CB, c = t % CB;
-        const int pi = ti * CB + r, pj = tj * CB + c;
-        if (pi < npos && pj < npos && pj <= pi) {
-          const int gi = chol_row_of(pi, c1, nband, arrow0), gj = chol_row_of(pj, c1, nband, arrow0);
-          if (gj < ns) {       // the rhs row has no column
-            double s = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (dst[u]) {
+          const int r = (tid + 256 * u) / CB, c = (tid + 256 * u) % CB;
+          double s = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < CB; ++k) s += sLi[r][k] * sLj[c][k];
-            A[(size_t)gi * lda + gj] -= s;
-          }
+          for (int k = 0; k < CB; ++k) s += sLi[r][k] * sLj[c][k];
+          *dst[u] = old[u] - s;
         }
       }
     }
+    PSFM_CHOL_TICK(3);
     __threadfence();
     grid.sync();
+    PSFM_CHOL_TICK(4);
   }
   if (blockIdx.x != 0) return;
   if (tid == 0) *a.fail = s_bad;
@@ -510,12 +783,29 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
     const int npos = nband + (ns - arrow0);          // rhs row excluded
     // partial sums: column c of the panel, rows strided over the 8 row-groups
     const int c = tid % CB, g = tid / CB;
+    for (int t = tid; t < w * w; t += 256) {
+      const int r = t / w, cc = t % w;
+      if (cc <= r) sD[r][cc] = A[(size_t)(c0 + r) * lda + c0 + cc];
+    }
     double s = 0.0;
-    if (c < w)
-      for (int pos = g; pos < npos; pos += 8) {
+    if (c < w) {
+      int pos = g;
+      for (; pos + 24 < npos; pos += 32) {       // four independent loads in flight
+        double av[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = chol_row_of(pos + 8 * u, c1, nband, arrow0);
+          av[u] = A[(size_t)r * lda + c0 + c];
+          xv[u] = a.x[r];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s += av[u] * xv[u];
+      }
+      for (; pos < npos; pos += 8) {
         const int r = chol_row_of(pos, c1, nband, arrow0);
         s += A[(size_t)r * lda + c0 + c] * a.x[r];
       }
+    }
     sacc[g][c] = s;
     __syncthreads();
     if (tid < w) {
@@ -524,21 +814,20 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
       sacc[0][tid] = a.x[c0 + tid] - t;
     }
     __syncthreads();
-    // in-panel backward substitution (warp 0)
+    // in-panel backward substitution (warp 0; L11 staged in shared memory above)
     if (tid < CB) {
+      double mine = (tid < w) ? sacc[0][tid] : 0.0;
+      const double dinv = (tid < w) ? 1.0 / sD[tid][tid] : 0.0;
       for (int j = w - 1; j >= 0; --j) {
-        double v = 0.0;
-        if (tid == j) {
-          v = sacc[0][j] / A[(size_t)(c0 + j) * lda + c0 + j];
-          a.x[c0 + j] = v;
-        }
-        v = __shfl_sync(0xffffffffu, v, j);
-        if (tid < j) sacc[0][tid] -= A[(size_t)(c0 + j) * lda + c0 + tid] * v;
-        __syncwarp();
+        const double v = __shfl_sync(0xffffffffu, mine * dinv, j);
+        if (tid == j) a.x[c0 + j] = v;
+        if (tid < j) mine -= sD[j][tid] * v;
       }
     }
     __syncthreads();
   }
+  PSFM_CHOL_TICK(5);
+#undef PSFM_CHOL_TICK
 }
 
 }  // namespace ba

@@ -139,7 +139,8 @@ __device__ inline void quat_plus(const double* x, const double* d, double* o) {
 struct CamFinArgs {
   const double* lin_cam;    // [F][NVL]  F'F blocks, F'r
   const double* lin_intr;   // [C][NVI]
-  const double* prep_cam;   // [F][NVL]  -(W hinv W') blocks, -(W w)
+  const double* prep_cam;   // [F][prep_stride]  -(W hinv W') blocks at 0 (when prep_blocks), -(W w) at prep_goff
+  int prep_stride, prep_goff, prep_blocks;   // k_schur_prep: NVL, 12, 1;  k_schur_tile sums: NVX2, 21, 0
   const double* prep_intr;  // [C][NVI]
   const unsigned char* active;  // [NS]
   const double* scale_c;        // [NS] jacobi scaling (0 on inactive slots)
@@ -161,8 +162,8 @@ __global__ void k_cam_finalize(const CamFinArgs a) {
     const int img = nb >> 1, b = nb & 1;
     A = a.lin_cam + (size_t)img * NVL + 6 * b;
     g = a.lin_cam + (size_t)img * NVL + 12 + 3 * b;
-    Cc = a.prep_cam + (size_t)img * NVL + 6 * b;
-    gc = a.prep_cam + (size_t)img * NVL + 12 + 3 * b;
+    Cc = a.prep_blocks ? a.prep_cam + (size_t)img * a.prep_stride + 6 * b : nullptr;
+    gc = a.prep_cam + (size_t)img * a.prep_stride + a.prep_goff + 3 * b;
     slot0 = 6 * img + 3 * b;
   } else {
     const int c = nb - 2 * a.F;
@@ -178,7 +179,7 @@ __global__ void k_cam_finalize(const CamFinArgs a) {
   // the tile kernels accumulate with the UNSCALED Jacobian: apply diag(s) on both sides here
   const double ss[6] = {sc[0] * sc[0], sc[0] * sc[1], sc[0] * sc[2], sc[1] * sc[1], sc[1] * sc[2], sc[2] * sc[2]};
   double Mb[6];
-  for (int k = 0; k < 6; ++k) Mb[k] = ss[k] * (A[k] + Cc[k]);
+  for (int k = 0; k < 6; ++k) Mb[k] = ss[k] * (A[k] + (Cc ? Cc[k] : 0.0));
   for (int j = 0; j < 3; ++j) {
     double d2 = 0.0;
     if (act[j]) d2 = fmin(fmax(ss[dg[j]] * A[dg[j]], a.min_diag), a.max_diag) / a.radius;

@@ -93,8 +93,16 @@ struct psfm_ba_solver {
   long long npairs = 0;
   DBuf<unsigned long long> d_entries;
   DBuf<int> d_blk_key, d_chunk_blk, d_cholfail;
+  DBuf<unsigned long long> d_cholprof;
   DBuf<long long> d_chunk_beg;
   DBuf<double> d_W, d_WH, d_xcam, d_xcamrep, d_Sblk, d_S;
+  // fused tile path (k_schur_tile): tile-local pair tasks and the band-block accumulator
+  bool fused = false;
+  int span = 0, ntasks = 0, band_nrep = 1;
+  size_t band_n = 0;
+  DBuf<unsigned int> d_tentries;
+  DBuf<int> d_task_slot, d_task_beg, d_tile_task;
+  DBuf<double> d_xband, d_bandrep;      // d_xband = [xcam F*NVX2 | Sband band_n] (one all-reduce)
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   cudaStream_t stream = nullptr;
@@ -483,22 +491,34 @@ void do_cam_gmax(psfm_ba_solver* S) {
 }
 
 // reduced system: Schur-Jacobi blocks, rhs, LM diagonal
-void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius) {
+void cam_finalize(psfm_ba_solver* S, const RunCfg& c, double radius, bool fused) {
+  CamFinArgs f;
+  f.lin_cam = S->d_lin.p; f.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
+  if (fused) { f.prep_cam = S->d_xband.p; f.prep_stride = NVX2; f.prep_goff = 21; f.prep_blocks = 0; }
+  else { f.prep_cam = S->d_prep.p; f.prep_stride = NVL; f.prep_goff = 12; f.prep_blocks = 1; }
+  f.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
+  f.active = S->d_active.p; f.scale_c = S->d_scale_c.p; f.radius = radius; f.min_diag = c.o.min_lm_diagonal; f.max_diag = c.o.max_lm_diagonal;
+  f.F = S->F; f.C = S->C; f.Dc2 = S->d_Dc2.p; f.Minv = S->d_Minv.p; f.rhs = S->d_rhs.p;
+  k_cam_finalize<<<(S->NB + 127) / 128, 128, 0, S->stream>>>(f);
+  PSFM_LAUNCH_CHECK();
+}
+
+// fused_explicit: the rhs correction comes out of k_schur_tile (do_explicit_solve_fused), the
+// Schur-Jacobi blocks are not needed; only the point blocks and the intrinsics sums are made here
+void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius, bool fused_explicit = false) {
   S->d_prep.zero(S->stream);
   do_point_blocks(S, c, radius);
+  if (fused_explicit) {
+    dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
+    return;
+  }
   PrepArgs a;
   a.L = lin_of(S); a.pose16 = S->d_pose16.p; a.X = S->d_X[S->cur].p; a.ht = S->d_hinv.p; a.wt = S->d_w.p;
   a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL;
   PSFM_TILE_LAUNCH(k_schur_prep, 18, 12, S, c.rot, a);
   fold_replicas(S, S->d_prep.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr, nullptr);
   dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
-  CamFinArgs f;
-  f.lin_cam = S->d_lin.p; f.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
-  f.prep_cam = S->d_prep.p; f.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
-  f.active = S->d_active.p; f.scale_c = S->d_scale_c.p; f.radius = radius; f.min_diag = c.o.min_lm_diagonal; f.max_diag = c.o.max_lm_diagonal;
-  f.F = S->F; f.C = S->C; f.Dc2 = S->d_Dc2.p; f.Minv = S->d_Minv.p; f.rhs = S->d_rhs.p;
-  k_cam_finalize<<<(S->NB + 127) / 128, 128, 0, S->stream>>>(f);
-  PSFM_LAUNCH_CHECK();
+  cam_finalize(S, c, radius, false);
 }
 
 void scale_vec(psfm_ba_solver* S, const double* x, const int* skip_flag) {
@@ -695,6 +715,65 @@ void ensure_pairs(psfm_ba_solver* S) {
     DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
     cub::DeviceScan::ExclusiveSum(tmp.p, need, cnt.p, ptr32.p, M + 1, st);
   }
+  S->span = (S->bw - 5) / 6;
+  {
+    const size_t smem256 = TileSmem<256>::bytes(WW, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(WW, 15, S->cap_ns, S->cap_np);
+    const size_t smem = S->tile == 256 ? smem256 : smem512;
+    S->fused = S->tile <= 512 && smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
+  }
+  if (S->fused) {
+    // ---- tile-local tasks for k_schur_tile
+    const int T = S->T;
+    int fb = 1; while ((1 << fb) < F) ++fb;
+    int tb = 1; while ((1ll << tb) < (long long)T + 1) ++tb;
+    DBuf<unsigned long long> k64, k64_out, uk64;
+    DBuf<unsigned int> v32;
+    k64.alloc(NPr, st); k64_out.alloc(NPr, st); v32.alloc(NPr, st); S->d_tentries.alloc(NPr, st);
+    k_pair_fill_tile<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, ptr32.p, M,
+                                                   S->d_tile_start.p, T, fb, k64.p, v32.p);
+    PSFM_LAUNCH_CHECK();
+    {
+      size_t need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, 0, tb + 2 * fb, st);
+      DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+      cub::DeviceRadixSort::SortPairs(tmp.p, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, 0, tb + 2 * fb, st);
+    }
+    k64.release(); v32.release();
+    uk64.alloc(NPr, st); ucount.alloc(NPr + 1, st); nruns.alloc(1, st);
+    {
+      size_t need = 0;
+      cub::DeviceRunLengthEncode::Encode(nullptr, need, k64_out.p, uk64.p, ucount.p, nruns.p, (int)NPr, st);
+      DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+      cub::DeviceRunLengthEncode::Encode(tmp.p, need, k64_out.p, uk64.p, ucount.p, nruns.p, (int)NPr, st);
+    }
+    int nt = 0;
+    PSFM_CUDA(cudaMemcpyAsync(&nt, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->ntasks = nt;
+    S->d_task_slot.alloc(nt, st); S->d_task_beg.alloc((size_t)nt + 1, st); S->d_tile_task.alloc((size_t)T + 1, st);
+    PSFM_CUDA(cudaMemsetAsync(ucount.p + nt, 0, sizeof(int), st));
+    {
+      size_t need = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, ucount.p, S->d_task_beg.p, nt + 1, st);
+      DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+      cub::DeviceScan::ExclusiveSum(tmp.p, need, ucount.p, S->d_task_beg.p, nt + 1, st);
+    }
+    if (nt) { k_task_slots<<<grid_for(nt), 256, 0, st>>>(uk64.p, nt, fb, S->span, S->d_task_slot.p); PSFM_LAUNCH_CHECK(); }
+    k_tile_tasks<<<grid_for((size_t)T + 1), 256, 0, st>>>(uk64.p, nt, fb, T, S->d_tile_task.p);
+    PSFM_LAUNCH_CHECK();
+    S->band_n = (size_t)F * (S->span + 1) * 36;
+    int nrep = NREP;
+    while (nrep > 1 && S->band_n * nrep * sizeof(double) > ((size_t)256 << 20)) nrep >>= 1;
+    S->band_nrep = nrep;
+    S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
+    S->d_bandrep.alloc(S->band_n * nrep, st); S->d_bandrep.zero(st);
+    S->d_xcamrep.alloc((size_t)NREP * F * NVX2, st); S->d_xcamrep.zero(st);
+    S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), st); S->d_cholfail.alloc(1, st);
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->pairs_ready = true;
+    tm.mark("tile pair tasks (explicit Schur, fused)");
+    return;
+  }
   keys.alloc(NPr, st); keys_out.alloc(NPr, st); vals.alloc(NPr, st); S->d_entries.alloc(NPr, st);
   k_pair_fill<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, ptr32.p, M, F, keys.p, vals.p);
   PSFM_LAUNCH_CHECK();
@@ -747,6 +826,86 @@ void ensure_pairs(psfm_ba_solver* S) {
   tm.mark("pair structure (explicit Schur)");
 }
 
+// blocked band(+arrow) Cholesky of d_S (rhs carried as the extra row) -> d_x; false on a bad pivot
+bool launch_cholesky(psfm_ba_solver* S) {
+  cudaStream_t st = S->stream;
+  const int nbnd = 6 * S->F;
+  const int bw = std::min(S->bw, nbnd);
+  {
+    static int grid_limit = 0;
+    if (grid_limit == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      PSFM_CUDA(cudaGetDevice(&dev));
+      PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_blocked, 256, 0));
+      grid_limit = std::max(1, sms * std::min(per_sm, 1));
+    }
+    CholArgs ca;
+    ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
+    static const bool want_prof = getenv("PSFM_CHOL_PROFILE") != nullptr;
+    if (want_prof && S->d_cholprof.n == 0) { S->d_cholprof.alloc(8, st); S->d_cholprof.zero(st); }
+    ca.prof = want_prof ? S->d_cholprof.p : nullptr;
+    void* kargs[] = {(void*)&ca};
+    // few CTAs when the band is narrow (cheaper grid barriers), all SMs for a dense system
+    const int tiles = (std::min(bw + 2, nbnd) + (S->NS + 1 - nbnd) + CB - 1) / CB;
+    const int grid = std::max(1, std::min(grid_limit, tiles * (tiles + 1) / 2));
+    PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid), dim3(256), kargs, 0, st));
+    PSFM_LAUNCH_CHECK();
+  }
+  { cudaEvent_t e = S->events.get(); PSFM_CUDA(cudaEventRecord(e, st)); S->ev_chol.back().second = e; }
+  int fail = 0;
+  PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PSFM_CUDA(cudaStreamSynchronize(st));
+  if (S->d_cholprof.n) {   // debugging aid: cumulative SM cycles of CTA 0 per phase
+    unsigned long long h[8];
+    PSFM_CUDA(cudaMemcpy(h, S->d_cholprof.p, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[psfm chol cycles] diag %llu rows %llu sync %llu trail %llu sync %llu backsub %llu\n",
+            h[0], h[1], h[2], h[3], h[4], h[5]);
+  }
+  return fail == 0;
+}
+
+
+// exact reduced-system solve, fused tile path: k_schur_tile -> band blocks -> dense S -> Cholesky
+bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) {
+  cudaStream_t st = S->stream;
+  const size_t nx = (size_t)S->F * NVX2;
+  StArgs w;
+  w.L = lin_of(S); w.pose16 = S->d_pose16.p; w.X = S->d_X[S->cur].p; w.ht = S->d_hinv.p; w.wt = S->d_w.p; w.wk = S->d_wk.p;
+  w.K = S->d_K[S->cur].p; w.acc_cam = S->d_xcamrep.p; w.rep_stride = nx; w.intr = c.intr;
+  w.entries = S->d_tentries.p; w.task_slot = S->d_task_slot.p; w.task_beg = S->d_task_beg.p; w.tile_task = S->d_tile_task.p;
+  w.Sband = S->d_bandrep.p; w.band_stride = S->band_n; w.nrep_mask = S->band_nrep - 1;
+  auto mark = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, bool begin) {
+    cudaEvent_t e = S->events.get();
+    PSFM_CUDA(cudaEventRecord(e, st));
+    if (begin) v.push_back({e, nullptr}); else v.back().second = e;
+  };
+  mark(S->ev_sw, true);
+  PSFM_TILE_LAUNCH(k_schur_tile, WW, 15, S, c.rot, w);
+  mark(S->ev_sw, false);
+  mark(S->ev_chol, true);
+  fold_replicas(S, S->d_xband.p, S->d_xcamrep.p, nx, nullptr, nullptr);
+  k_fold_replicas<<<grid_for(S->band_n), 256, 0, st>>>(S->d_xband.p + nx, S->d_bandrep.p, S->band_n, S->band_n, S->band_nrep, nullptr, nullptr);
+  PSFM_LAUNCH_CHECK();
+  dist::allreduce_sum(S->d_xband.p, S->d_xband.n, st);
+  cam_finalize(S, c, radius, true);
+  S->d_S.zero(st);
+  BandAsmArgs ba_;
+  ba_.Sband = S->d_xband.p + nx; ba_.scale_c = S->d_scale_c.p; ba_.F = S->F; ba_.span = S->span; ba_.lda = S->NS + 1; ba_.S = S->d_S.p;
+  k_schur_assemble_band<<<grid_for(S->band_n), 256, 0, st>>>(ba_); PSFM_LAUNCH_CHECK();
+  AsmArgs a;
+  a.Sblk = nullptr; a.blk_key = nullptr; a.nblocks = 0;
+  a.lin_cam = S->d_lin.p; a.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
+  a.prep_intr = S->d_prep.p + (size_t)S->F * NVL; a.xcam = S->d_xband.p; a.xstride = NVX2;
+  a.scale_c = S->d_scale_c.p; a.Dc2 = S->d_Dc2.p; a.active = S->d_active.p;
+  a.rhs = S->d_rhs.p;
+  a.F = S->F; a.C = S->C; a.NS = S->NS; a.lda = S->NS + 1; a.S = S->d_S.p;
+  k_schur_assemble_local<<<grid_for(S->F, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
+  return launch_cholesky(S);
+}
+
 // exact reduced-system solve: explicit S, banded Cholesky; solution in d_x. returns false on failure
 bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   ensure_pairs(S);
@@ -776,7 +935,7 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   AsmArgs a;
   a.Sblk = S->d_Sblk.p; a.blk_key = S->d_blk_key.p; a.nblocks = S->nblocks;
   a.lin_cam = S->d_lin.p; a.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
-  a.prep_intr = S->d_prep.p + (size_t)S->F * NVL; a.xcam = S->d_xcam.p;
+  a.prep_intr = S->d_prep.p + (size_t)S->F * NVL; a.xcam = S->d_xcam.p; a.xstride = NVX;
   a.scale_c = S->d_scale_c.p; a.Dc2 = S->d_Dc2.p; a.active = S->d_active.p;
   a.rhs = S->d_rhs.p;
   a.F = S->F; a.C = S->C; a.NS = S->NS; a.lda = S->NS + 1; a.S = S->d_S.p;
@@ -785,38 +944,13 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   dist::allreduce_sum(S->d_S.p, S->d_S.n, st);
   k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
-  const int nbnd = 6 * S->F;
-  const int bw = std::min(S->bw, nbnd);
-  {
-    static int grid_limit = 0;
-    if (grid_limit == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
-      PSFM_CUDA(cudaGetDevice(&dev));
-      PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_blocked, 256, 0));
-      grid_limit = std::max(1, sms * std::min(per_sm, 1));
-    }
-    CholArgs ca;
-    ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
-    void* kargs[] = {(void*)&ca};
-    // few CTAs when the band is narrow (cheaper grid barriers), all SMs for a dense system
-    const int tiles = (std::min(bw + 2, nbnd) + (S->NS + 1 - nbnd) + CB - 1) / CB;
-    const int grid = std::max(1, std::min(grid_limit, tiles * (tiles + 1) / 2));
-    PSFM_CUDA(cudaLaunchCooperativeKernel((void*)k_chol_blocked, dim3(grid), dim3(256), kargs, 0, st));
-    PSFM_LAUNCH_CHECK();
-  }
-  mark(S->ev_chol, false);
-  int fail = 0;
-  PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PSFM_CUDA(cudaStreamSynchronize(st));
-  return fail == 0;
+  return launch_cholesky(S);
 }
 
 // LevenbergMarquardtStrategy::ComputeStep + ComputeCandidatePointAndEvaluateCost
 StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* nprod) {
   StepOut so;
   memset(&so, 0, sizeof(so));
-  do_reduced_setup(S, c, radius);
   int max_it, iters = 0;
   double q_tol, r_tol;
   if (c.solver == PSFM_BA_SOLVER_ITERATIVE_SCHUR) {
@@ -828,8 +962,11 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   }
   const bool explicit_ok = c.solver == PSFM_BA_SOLVER_EXACT_SCHUR && c.intr <= 1 && !getenv("PSFM_EXACT_PCG") &&
                            (size_t)S->NS * S->NS * sizeof(double) <= ((size_t)4 << 30);
+  if (explicit_ok) ensure_pairs(S);
+  const bool fused = explicit_ok && S->fused;
+  do_reduced_setup(S, c, radius, fused);
   if (explicit_ok) {
-    so.pcg_flag = do_explicit_solve(S, c) ? PCG_SUCCESS : PCG_FAILURE;
+    so.pcg_flag = (fused ? do_explicit_solve_fused(S, c, radius) : do_explicit_solve(S, c)) ? PCG_SUCCESS : PCG_FAILURE;
     iters = 1;
   } else {
     so.pcg_flag = do_pcg(S, c, q_tol, r_tol, max_it, &iters, nprod);
@@ -1006,7 +1143,8 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
   for (auto& e : S->ev_sw) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_w_ms += ms; }
   for (auto& e : S->ev_pairs) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.schur_pairs_ms += ms; }
   for (auto& e : S->ev_chol) { PSFM_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); s.cholesky_ms += ms; }
-  s.num_explicit_solves = (int)S->ev_pairs.size();
+  s.num_explicit_solves = (int)S->ev_chol.size();
+  s.num_pair_entries = S->npairs; s.num_pair_tasks = S->ntasks; s.explicit_fused = S->fused ? 1 : 0;
   s.num_linearize = (int)S->ev_lin.size();
   s.num_schur_products = (int)S->ev_sp.size();
   s.num_iterations = iteration;

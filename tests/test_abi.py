@@ -20,7 +20,7 @@ def test_header_symbols_exported():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in psfm_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert L.psfm_abi_version() == 1
+    assert L.psfm_abi_version() == 2
 
 
 def test_struct_layouts_match_defaults():
