@@ -308,25 +308,15 @@ struct LinArgs {
   double* acc_cost;       // [1]
 };
 
+// One tile of the Jacobian sweep.  Shared memory (sm.simg, sm.spt, sm.pstart, sm.coff, sm.cimg,
+// sm.perm) holds the tile's staged inputs and is synchronised; ls / lp / xy are this thread's
+// observation.  Ends without a barrier.
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize(const TileCtx tc, const LinArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE> sm;
-  sm.carve(smem_raw, 18, 3, tc.cap_ns, tc.cap_np);
-  const TileInfo ti = tile_header(tc);
+__device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs& a, TileSmem<TILE>& sm, const TileInfo& ti,
+                                               const bool act, const int ls, const int lp, const double2 xy, const int rep) {
   const int tid = threadIdx.x;
-  const bool act = tid < ti.n;
   const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
-  int ls = 0, lp = 0;
-  double2 xy = make_double2(0.0, 0.0);
-  if (act) {
-    ls = __ldg(tc.obs_lseg + i);
-    lp = __ldg(tc.obs_lpt + i);
-    xy = tc.obs_xy[i];
-  }
-  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, nullptr, nullptr, true);
-
   double r0 = 0, r1 = 0, cost = 0, a00 = 0, a02 = 0, a12 = 0, jf0 = 0, jf1 = 0, sq = 0;
   double jp0[3] = {0, 0, 0}, jp1[3] = {0, 0, 0};
   ObsGeom g;
@@ -426,7 +416,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize(const
   __syncthreads();
   {
     // components handled: ROT -> 0..17, else 6..11 and 15..17 (9 values); 7 is structurally 0
-    double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
+    double* dst = a.acc_cam + (size_t)(rep & (NREP - 1)) * a.rep_stride;
     const int nvc = ROT ? 18 : 9;
     for (int pair = tid; pair < nvc * ti.ns; pair += TILE) {
       int k = pair / ti.ns;
@@ -465,6 +455,26 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize(const
       else if (tid < 7) atomicAdd(a.acc_intr + 7 + (tid - 5), s2);
     }
   }
+}
+
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize(const TileCtx tc, const LinArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 18, 3, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
+  const int tid = threadIdx.x;
+  const bool act = tid < ti.n;
+  const size_t i = (size_t)ti.base + tid;
+  int ls = 0, lp = 0;
+  double2 xy = make_double2(0.0, 0.0);
+  if (act) {
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    xy = tc.obs_xy[i];
+  }
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, nullptr, nullptr, true);
+  linearize_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, xy, blockIdx.x);
 }
 
 // ------------------------------------------------------------------ K2: point blocks

@@ -19,6 +19,7 @@
 #include <cub/cub.cuh>
 
 #include "ba_kernels.cuh"
+#include "ba_tile_pipe.cuh"
 
 namespace psfm {
 namespace ba {
@@ -245,27 +246,13 @@ struct StArgs {
   int nrep_mask;
 };
 
+// One tile of the fused Schur kernel; shared memory holds the staged inputs (see linearize_tile).
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(const TileCtx tc, const StArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE> sm;
-  sm.carve(smem_raw, WW, 15, tc.cap_ns, tc.cap_np);
-  const TileInfo ti = tile_header(tc);
+__device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs& a, TileSmem<TILE>& sm, const TileInfo& ti,
+                                                const bool act, const int ls, const int lp, const double a00, const double a02,
+                                                const double a12, const int rep, const int t0, const int nt) {
   const int tid = threadIdx.x;
-  const bool act = tid < ti.n;
-  const size_t M = tc.M;
-  const size_t i = (size_t)ti.base + tid;
-  int ls = 0, lp = 0;
-  double a00 = 0, a02 = 0, a12 = 0;
-  if (act) {
-    ls = __ldg(tc.obs_lseg + i);
-    lp = __ldg(tc.obs_lpt + i);
-    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
-  }
-  const int t0 = __ldg(a.tile_task + blockIdx.x), nt = __ldg(a.tile_task + blockIdx.x + 1) - t0;
   const double inv_f = (a.intr >= 1) ? 1.0 / __ldg(a.K) : 0.0;
-  // per point: X (0..2), H~ (3..8), focal row of G'E (9..11), w^ (12..14)
-  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wk, true, a.wt);
   double* sv = sm.sv + tid;
 #pragma unroll
   for (int k = 0; k < NVX2; ++k) sv[k * TILE] = 0.0;
@@ -326,7 +313,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(cons
   }
   __syncthreads();
   {
-    double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
+    double* dst = a.acc_cam + (size_t)(rep & (NREP - 1)) * a.rep_stride;
     tile_reduce_images<TILE>(sm, ti, NVX2, [&](int k, int img, double acc) {
       if (acc != 0.0) atomicAdd(dst + (size_t)img * NVX2 + k, acc);
     });
@@ -342,7 +329,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(cons
       for (int k = 0; k < 3; ++k) { o[3 * r + k] = W[r][k]; o[18 + 3 * r + k] = WH[r][k]; }
   }
   __syncthreads();
-  double* band = a.Sband + (size_t)(blockIdx.x & a.nrep_mask) * a.band_stride;
+  double* band = a.Sband + (size_t)(rep & a.nrep_mask) * a.band_stride;
   const int nq = ROT ? 2 * nt : nt;
   for (int q = tid; q < nq; q += TILE) {
     const int t = t0 + (ROT ? (q >> 1) : q), half = ROT ? (q & 1) : 1;
@@ -369,6 +356,59 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(cons
 #pragma unroll
     for (int k = 0; k < 18; ++k) atomicAdd(dst + k, acc[k]);
   }
+}
+
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(const TileCtx tc, const StArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, WW, 15, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
+  const int tid = threadIdx.x;
+  const bool act = tid < ti.n;
+  const size_t M = tc.M;
+  const size_t i = (size_t)ti.base + tid;
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0;
+  if (act) {
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
+  }
+  const int t0 = __ldg(a.tile_task + blockIdx.x), nt = __ldg(a.tile_task + blockIdx.x + 1) - t0;
+  // per point: X (0..2), H~ (3..8), focal row of G'E (9..11), w^ (12..14)
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wk, true, a.wt);
+  schur_tile_body<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, blockIdx.x, t0, nt);
+}
+
+// persistent, pipelined form (ba_tile_pipe.cuh): the inputs of the next tile are in flight
+// (cp.async) while this tile's pair tasks run
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile_p(const TileCtx tc, const PipeSrc ps, const StArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int4 hdr_ring[4][2];
+  const int cns = tc.cap_ns, cnp = tc.cap_np;
+  const size_t sb = PipeStage<TILE>::bytes(false, true, 15, cns, cnp);
+  TileSmem<TILE> sm;
+  sm.cap_ns = cns; sm.cap_np = cnp;
+  sm.sv = reinterpret_cast<double*>(smem_raw + 2 * sb);
+  sm.sw = nullptr; sm.sred = nullptr; sm.sx = nullptr;
+  pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, 15, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
+    view_stage<TILE>(sm, s, ti.base);
+    const int tid = threadIdx.x;
+    const bool act = tid < ti.n;
+    const int off = ti.base & 1;
+    int ls = 0, lp = 0;
+    double a00 = 0, a02 = 0, a12 = 0;
+    if (act) { ls = s.lseg[off + tid]; lp = s.lpt[off + tid]; a00 = s.a[tid]; a02 = s.a[TILE + tid]; a12 = s.a[2 * TILE + tid]; }
+    const int t0 = __ldg(a.tile_task + tile), nt = __ldg(a.tile_task + tile + 1) - t0;
+    schur_tile_body<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, tile, t0, nt);
+  });
+}
+
+template <int TILE>
+inline size_t pipe_smem_schur_tile(int cns, int cnp) {
+  return 2 * PipeStage<TILE>::bytes(false, true, 15, cns, cnp) + sizeof(double) * WW * TILE;
 }
 
 // ---- tile-local pair structure (built once per problem)

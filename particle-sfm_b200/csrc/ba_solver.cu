@@ -78,6 +78,12 @@ struct psfm_ba_solver {
   DBuf<unsigned short> d_tile_perm, d_cseg_off, d_obs_lseg, d_obs_lpt;
   DBuf<int> d_obs_orig;
   DBuf<double2> d_obs_xy;
+  // pipeline form of the structure (ba_tile_pipe.cuh)
+  bool pipe = false;
+  int sm_count = 0;
+  DBuf<int4> d_tile_hdr;
+  DBuf<int> d_pstart_rel, d_cseg_off32;
+  DBuf<double> d_seg_pose;
   DBuf<unsigned char> d_active;
   // device state
   DBuf<double> d_pose[2], d_X[2], d_K[2];
@@ -105,6 +111,7 @@ struct psfm_ba_solver {
   DBuf<double> d_xband, d_bandrep;      // d_xband = [xcam F*NVX2 | Sband band_n] (one all-reduce)
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
+  double* pin_state = nullptr;     // pinned staging of the state: pose (8F) | X (3P) | K (3C)
   cudaStream_t stream = nullptr;
   EventPool events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lin, ev_sp, ev_sw, ev_pairs, ev_chol;
@@ -122,6 +129,7 @@ struct psfm_ba_solver {
   ~psfm_ba_solver() {
     if (stream) cudaStreamSynchronize(stream);
     if (hs) cudaFreeHost(hs);
+    if (pin_state) cudaFreeHost(pin_state);
   }
 };
 
@@ -253,7 +261,7 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   tm.mark("tiles (host greedy)");
   // sort observations by (internal point, image); radix sort is stable => ties keep input order
   S->d_obs_img.alloc(M, st); S->d_obs_pt.alloc(M, st); S->d_obs_xy.alloc(M, st); S->d_obs_orig.alloc(M, st);
-  S->d_tile_perm.alloc(M, st); S->d_obs_lseg.alloc(M, st); S->d_obs_lpt.alloc(M, st);
+  S->d_tile_perm.alloc((size_t)M + 2, st); S->d_obs_lseg.alloc((size_t)M + 2, st); S->d_obs_lpt.alloc((size_t)M + 2, st);
   S->d_cseg_ptr.alloc((size_t)T + 1, st);
   if (M) {
     k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
@@ -294,6 +302,21 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
     else k_st_tile_segments<1024><<<T, 1024, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
     PSFM_LAUNCH_CHECK();
   }
+  // pipeline form: packed tile headers, tile-relative point starts, 32-bit segment offsets
+  S->pipe = T > 0 && !getenv("PSFM_NO_PIPE");
+  if (S->pipe) {
+    int dev = 0;
+    PSFM_CUDA(cudaGetDevice(&dev));
+    PSFM_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    S->d_tile_hdr.alloc(2 * (size_t)T, st); S->d_pstart_rel.alloc((size_t)P + 1, st);
+    S->d_cseg_off32.alloc((size_t)S->nseg + 1, st); S->d_seg_pose.alloc(12 * (size_t)S->nseg + 2, st);
+    k_pipe_headers<<<grid_for(T), 256, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_cseg_ptr.p, T, S->d_tile_hdr.p);
+    PSFM_LAUNCH_CHECK();
+    k_pipe_pstart<<<T, 128, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_pt_ptr.p, T, S->d_pstart_rel.p);
+    PSFM_LAUNCH_CHECK();
+    k_pipe_off32<<<grid_for(S->nseg), 256, 0, st>>>(S->d_cseg_off.p, S->nseg, S->d_cseg_off32.p);
+    PSFM_LAUNCH_CHECK();
+  }
   PSFM_CUDA(cudaStreamSynchronize(st));
   tm.mark("sort + tile order (device)");
   return PSFM_OK;
@@ -318,6 +341,7 @@ void alloc_work(psfm_ba_solver* S) {
   S->d_pcg.alloc(1, S->stream);
   PSFM_CUDA(cudaMallocHost((void**)&S->hs, sizeof(HostScalars)));
   memset(S->hs, 0, sizeof(HostScalars));
+  PSFM_CUDA(cudaMallocHost((void**)&S->pin_state, sizeof(double) * (8 * F + 3 * P + 3 * C + 1)));
 }
 
 // ---------------------------------------------------------------- kernel dispatch
@@ -344,6 +368,32 @@ void alloc_work(psfm_ba_solver* S) {
       else { if (ROT) _go(integral_constant<int, 1024>{}, std::true_type{}); else _go(integral_constant<int, 1024>{}, std::false_type{}); } \
       PSFM_LAUNCH_CHECK();                                                                                 \
     }                                                                                                      \
+  } while (0)
+
+// persistent pipelined tile kernels: grid = SMs x resident CTAs (capped by the tile count)
+#define PSFM_PIPE_LAUNCH(KERNEL, SMEM_FN, S, ROT, PS, ARGS)                                                 \
+  do {                                                                                                     \
+    const TileCtx _tc = (S)->tc();                                                                         \
+    auto _go = [&](auto tile_c, auto rot_c) {                                                              \
+      constexpr int TL = decltype(tile_c)::value;                                                          \
+      constexpr bool RT = decltype(rot_c)::value;                                                          \
+      const size_t smem = SMEM_FN<TL>((S)->cap_ns, (S)->cap_np);                                           \
+      static size_t attr_bytes = 0;                                                                        \
+      static int occ = 0;                                                                                  \
+      if (smem > attr_bytes || occ == 0) {                                                                 \
+        PSFM_CUDA(cudaFuncSetAttribute(KERNEL<TL, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                       (int)smem));                                                        \
+        PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL<TL, RT>, TL, smem));          \
+        if (occ < 1) occ = 1;                                                                              \
+        attr_bytes = smem;                                                                                 \
+      }                                                                                                    \
+      const int grid = std::min((S)->T, (S)->sm_count * occ);                                              \
+      KERNEL<TL, RT><<<grid, TL, smem, (S)->stream>>>(_tc, PS, ARGS);                                      \
+    };                                                                                                     \
+    using std::integral_constant;                                                                          \
+    if ((S)->tile == 256) { if (ROT) _go(integral_constant<int, 256>{}, std::true_type{}); else _go(integral_constant<int, 256>{}, std::false_type{}); } \
+    else { if (ROT) _go(integral_constant<int, 512>{}, std::true_type{}); else _go(integral_constant<int, 512>{}, std::false_type{}); } \
+    PSFM_LAUNCH_CHECK();                                                                                   \
   } while (0)
 
 struct RunCfg {
@@ -396,8 +446,10 @@ int resolve_cfg(psfm_ba_solver* S, const psfm_ba_options* opts, RunCfg& c) {
 }
 
 void upload_state(psfm_ba_solver* S) {
-  const int F = S->F, P = S->P;
-  std::vector<double> pose(8 * (size_t)F, 0.0), X(3 * (size_t)P);
+  const int F = S->F, P = S->P, C = S->C;
+  double* pose = S->pin_state;
+  double* X = pose + 8 * (size_t)F;
+  double* K = X + 3 * (size_t)P;
   for (int i = 0; i < F; ++i) {
     // image.NormalizeQvec() — bundle_adjustment.cc:355
     double* q = &S->h_qvec[4 * (size_t)i];
@@ -406,29 +458,42 @@ void upload_state(psfm_ba_solver* S) {
     else for (int k = 0; k < 4; ++k) q[k] /= n;
     for (int k = 0; k < 4; ++k) pose[8 * (size_t)i + k] = q[k];
     for (int k = 0; k < 3; ++k) pose[8 * (size_t)i + 4 + k] = S->h_tvec[3 * (size_t)i + k];
+    pose[8 * (size_t)i + 7] = 0.0;
   }
-  for (int id = 0; id < P; ++id)
-    for (int k = 0; k < 3; ++k) X[3 * (size_t)id + k] = S->h_xyz[3 * (size_t)S->pt_orig[id] + k];
+  const int* po = S->pt_orig.data();
+  const double* hx = S->h_xyz.data();
+  for (int id = 0; id < P; ++id) {
+    const double* src = hx + 3 * (size_t)po[id];
+    X[3 * (size_t)id] = src[0]; X[3 * (size_t)id + 1] = src[1]; X[3 * (size_t)id + 2] = src[2];
+  }
+  for (int k = 0; k < 3 * C; ++k) K[k] = S->h_K[k];
   S->cur = 0;
-  S->d_pose[0].upload(pose.data(), pose.size(), S->stream);
-  S->d_X[0].upload(X.data(), X.size(), S->stream);
-  S->d_K[0].upload(S->h_K.data(), S->h_K.size(), S->stream);
+  S->d_pose[0].upload(pose, 8 * (size_t)F, S->stream);
+  S->d_X[0].upload(X, 3 * (size_t)P, S->stream);
+  S->d_K[0].upload(K, 3 * (size_t)C, S->stream);
   PSFM_CUDA(cudaStreamSynchronize(S->stream));
 }
 
 void download_state(psfm_ba_solver* S) {
-  const int F = S->F, P = S->P;
-  std::vector<double> pose(8 * (size_t)F), X(3 * (size_t)P);
-  PSFM_CUDA(cudaMemcpyAsync(pose.data(), S->d_pose[S->cur].p, pose.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
-  if (P) PSFM_CUDA(cudaMemcpyAsync(X.data(), S->d_X[S->cur].p, X.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
-  PSFM_CUDA(cudaMemcpyAsync(S->h_K.data(), S->d_K[S->cur].p, S->h_K.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  const int F = S->F, P = S->P, C = S->C;
+  double* pose = S->pin_state;
+  double* X = pose + 8 * (size_t)F;
+  double* K = X + 3 * (size_t)P;
+  PSFM_CUDA(cudaMemcpyAsync(pose, S->d_pose[S->cur].p, 8 * (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  if (P) PSFM_CUDA(cudaMemcpyAsync(X, S->d_X[S->cur].p, 3 * (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  PSFM_CUDA(cudaMemcpyAsync(K, S->d_K[S->cur].p, 3 * (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
   PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  for (int k = 0; k < 3 * C; ++k) S->h_K[k] = K[k];
   for (int i = 0; i < F; ++i) {
     for (int k = 0; k < 4; ++k) S->h_qvec[4 * (size_t)i + k] = pose[8 * (size_t)i + k];
     for (int k = 0; k < 3; ++k) S->h_tvec[3 * (size_t)i + k] = pose[8 * (size_t)i + 4 + k];
   }
-  for (int id = 0; id < P; ++id)
-    for (int k = 0; k < 3; ++k) S->h_xyz[3 * (size_t)S->pt_orig[id] + k] = X[3 * (size_t)id + k];
+  const int* po = S->pt_orig.data();
+  double* hx = S->h_xyz.data();
+  for (int id = 0; id < P; ++id) {
+    double* dst = hx + 3 * (size_t)po[id];
+    dst[0] = X[3 * (size_t)id]; dst[1] = X[3 * (size_t)id + 1]; dst[2] = X[3 * (size_t)id + 2];
+  }
 }
 
 Lin lin_of(psfm_ba_solver* S) {
@@ -447,6 +512,18 @@ void fold_replicas(psfm_ba_solver* S, double* dst, double* rep, size_t n, const 
   PSFM_LAUNCH_CHECK();
 }
 
+PipeSrc pipe_src(psfm_ba_solver* S) {
+  PipeSrc ps;
+  memset(&ps, 0, sizeof(ps));
+  ps.tile_hdr = S->d_tile_hdr.p; ps.obs_lseg = S->d_obs_lseg.p; ps.obs_lpt = S->d_obs_lpt.p; ps.tile_perm = S->d_tile_perm.p;
+  ps.pstart_rel = S->d_pstart_rel.p; ps.cseg_img = S->d_cseg_img.p; ps.cseg_off32 = S->d_cseg_off32.p;
+  ps.seg_pose = S->d_seg_pose.p; ps.X = S->d_X[S->cur].p;
+  return ps;
+}
+
+// the pipelined kernels need the tile inputs to fit twice in shared memory
+bool pipe_ok(psfm_ba_solver* S, size_t smem) { return S->pipe && S->tile <= 512 && smem <= (size_t)227 * 1024; }
+
 // Jacobian sweep at the current state (r, J, E'E, E'r, F'F blocks, F'r, cost)
 void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
   S->d_lin.zero(S->stream);
@@ -461,8 +538,19 @@ void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
   a.acc_cam = S->d_camrep.p; a.rep_stride = (size_t)S->F * NVL; a.acc_intr = S->d_lin.p + (size_t)S->F * NVL;
   a.acc_cost = S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const size_t pipe_smem = S->tile == 256 ? pipe_smem_linearize<256>(S->cap_ns, S->cap_np) : pipe_smem_linearize<512>(S->cap_ns, S->cap_np);
+  if (pipe_ok(S, pipe_smem)) {
+    k_seg_pose<<<grid_for(12 * (size_t)S->nseg), 256, 0, S->stream>>>(S->d_cseg_img.p, S->d_pose16.p, S->nseg, S->d_seg_pose.p);
+    PSFM_LAUNCH_CHECK();
+  }
   if (timed) { e0 = S->events.get(); e1 = S->events.get(); PSFM_CUDA(cudaEventRecord(e0, S->stream)); }
-  PSFM_TILE_LAUNCH(k_linearize, 18, 3, S, c.rot, a);
+  if (pipe_ok(S, pipe_smem)) {
+    PipeSrc ps = pipe_src(S);
+    ps.obs_xy = S->d_obs_xy.p;
+    PSFM_PIPE_LAUNCH(k_linearize_p, pipe_smem_linearize, S, c.rot, ps, a);
+  } else {
+    PSFM_TILE_LAUNCH(k_linearize, 18, 3, S, c.rot, a);
+  }
   if (timed) { PSFM_CUDA(cudaEventRecord(e1, S->stream)); S->ev_lin.push_back({e0, e1}); }
   fold_replicas(S, S->d_lin.p, S->d_camrep.p, (size_t)S->F * NVL, nullptr, nullptr);
   dist::allreduce_sum(S->d_lin.p, S->d_lin.n, S->stream);
@@ -881,7 +969,14 @@ bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
     if (begin) v.push_back({e, nullptr}); else v.back().second = e;
   };
   mark(S->ev_sw, true);
-  PSFM_TILE_LAUNCH(k_schur_tile, WW, 15, S, c.rot, w);
+  const size_t pipe_smem = S->tile == 256 ? pipe_smem_schur_tile<256>(S->cap_ns, S->cap_np) : pipe_smem_schur_tile<512>(S->cap_ns, S->cap_np);
+  if (pipe_ok(S, pipe_smem) && !getenv("PSFM_NO_PIPE_SCHUR")) {
+    PipeSrc ps = pipe_src(S);
+    ps.obs_a = S->d_a.p; ps.p6 = S->d_hinv.p; ps.p3a = S->d_wk.p; ps.p3b = S->d_w.p;
+    PSFM_PIPE_LAUNCH(k_schur_tile_p, pipe_smem_schur_tile, S, c.rot, ps, w);
+  } else {
+    PSFM_TILE_LAUNCH(k_schur_tile, WW, 15, S, c.rot, w);
+  }
   mark(S->ev_sw, false);
   mark(S->ev_chol, true);
   fold_replicas(S, S->d_xband.p, S->d_xcamrep.p, nx, nullptr, nullptr);
