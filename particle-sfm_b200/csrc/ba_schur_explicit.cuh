@@ -330,15 +330,25 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
   }
   __syncthreads();
   double* band = a.Sband + (size_t)(rep & a.nrep_mask) * a.band_stride;
-  const int nq = ROT ? 2 * nt : nt;
-  for (int q = tid; q < nq; q += TILE) {
-    const int t = t0 + (ROT ? (q >> 1) : q), half = ROT ? (q & 1) : 1;
-    const int e0 = __ldg(a.task_beg + t), e1 = __ldg(a.task_beg + t + 1);
+  // four lanes per task when rotations are free: (block rows 0-2 | 3-5) x (even | odd entries);
+  // the two entry parities are combined with one shuffle per element, each lane then issues
+  // nine of the eighteen REDs.  The trip count is uniform over the CTA (shuffles).
+  const int nq = (ROT ? 4 : 2) * nt;
+  for (int q0 = 0; q0 < nq; q0 += TILE) {
+    const int q = q0 + tid;
+    const bool valid = q < nq;
+    const int t = t0 + (ROT ? (q >> 2) : (q >> 1));
+    const int half = ROT ? ((q >> 1) & 1) : 1, par = q & 1;
+    int e0 = 0, e1 = 0;
+    if (valid) { e0 = __ldg(a.task_beg + t); e1 = __ldg(a.task_beg + t + 1); }
     double acc[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) acc[k] = 0.0;
-    for (int e = e0; e < e1; ++e) {
-      const unsigned int u = __ldg(a.entries + e);
+    int e = e0 + par;
+    unsigned int u_next = (e < e1) ? __ldg(a.entries + e) : 0u;
+    for (; e < e1; e += 2) {
+      const unsigned int u = u_next;
+      if (e + 2 < e1) u_next = __ldg(a.entries + e + 2);
       const double* A = sww + (size_t)(u >> 16) * WW + 18 + 9 * half;
       const double* B = sww + (size_t)(u & 0xffffu) * WW;
       double av[9], bv[18];
@@ -352,9 +362,13 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
         for (int c = 0; c < 6; ++c)
           acc[6 * r + c] += av[3 * r] * bv[3 * c] + av[3 * r + 1] * bv[3 * c + 1] + av[3 * r + 2] * bv[3 * c + 2];
     }
-    double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * half;
 #pragma unroll
-    for (int k = 0; k < 18; ++k) atomicAdd(dst + k, acc[k]);
+    for (int k = 0; k < 18; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    if (valid) {
+      double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * half + 9 * par;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(dst + k, par ? acc[9 + k] : acc[k]);
+    }
   }
 }
 

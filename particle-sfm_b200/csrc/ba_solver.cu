@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "ba_small_kernels.cuh"
@@ -54,6 +55,40 @@ struct HostScalars {   // pinned
 
 using namespace psfm;
 using namespace psfm::ba;
+
+// Pinned host staging is expensive to allocate (cudaMallocHost of 12 MB costs ~10 ms): buffers
+// are recycled across solver instances through a small process-wide free list.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  void* acquire(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_list.size(); ++i)
+        if (free_list[i].second >= bytes && (best < 0 || free_list[i].second < free_list[best].second)) best = i;
+      if (best >= 0) {
+        void* p = free_list[best].first;
+        *got = free_list[best].second;
+        free_list.erase(free_list.begin() + best);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    *got = bytes;
+    return p;
+  }
+  void release(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (free_list.size() < 8) { free_list.push_back({p, bytes}); return; }
+    cudaFreeHost(p);
+  }
+};
+PinnedPool g_pinned;
+}  // namespace
 
 struct StreamHolder {   // declared first in the solver => destroyed last (after every DBuf)
   cudaStream_t s = nullptr;
@@ -112,6 +147,7 @@ struct psfm_ba_solver {
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   double* pin_state = nullptr;     // pinned staging of the state: pose (8F) | X (3P) | K (3C)
+  size_t pin_state_bytes = 0, hs_bytes = 0;
   cudaStream_t stream = nullptr;
   EventPool events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lin, ev_sp, ev_sw, ev_pairs, ev_chol;
@@ -128,8 +164,8 @@ struct psfm_ba_solver {
   }
   ~psfm_ba_solver() {
     if (stream) cudaStreamSynchronize(stream);
-    if (hs) cudaFreeHost(hs);
-    if (pin_state) cudaFreeHost(pin_state);
+    g_pinned.release(hs, hs_bytes);
+    g_pinned.release(pin_state, pin_state_bytes);
   }
 };
 
@@ -339,9 +375,10 @@ void alloc_work(psfm_ba_solver* S) {
   S->d_camrep.alloc((size_t)NREP * F * NVL, S->stream); S->d_camrep.zero(S->stream);
   S->d_yrep.alloc((size_t)NREP * NS, S->stream); S->d_yrep.zero(S->stream);
   S->d_pcg.alloc(1, S->stream);
-  PSFM_CUDA(cudaMallocHost((void**)&S->hs, sizeof(HostScalars)));
+  S->hs = (HostScalars*)g_pinned.acquire(sizeof(HostScalars), &S->hs_bytes);
+  S->pin_state = (double*)g_pinned.acquire(sizeof(double) * (8 * F + 3 * P + 3 * C + 1), &S->pin_state_bytes);
+  if (!S->hs || !S->pin_state) { set_error("cudaMallocHost failed"); throw CudaFail{PSFM_ERR_CUDA}; }
   memset(S->hs, 0, sizeof(HostScalars));
-  PSFM_CUDA(cudaMallocHost((void**)&S->pin_state, sizeof(double) * (8 * F + 3 * P + 3 * C + 1)));
 }
 
 // ---------------------------------------------------------------- kernel dispatch
