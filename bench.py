@@ -235,27 +235,34 @@ def main():
     # Algorithmic bytes per launch (factored-Jacobian formulation):
     #   Jacobian sweep      read xy 16 + idx 4, write D 24 + r 16; per point X 24 r, E'E/E'r 72 w
     #   implicit S*p        read D 24 + idx 4; per point X 24 + H~ 48
-    #   W / W H~            read D 24 + idx 4, write 288; per point 120
-    #   pair products       every W and W H~ row once (288 B/obs) + 8 B/pair entry
+    #   fused Schur tile    read D 24 + idx 4; per point 120; 4 B per pair entry; 8 B per task
+    #   (unfused fallback)  W / W H~: read 28, write 288, per point 120; pairs: 288 B/obs + 8 B/entry
     peak, peak_src = read_peaks()
     M_local = prob.num_observations
     L = w["track_len"]
     pairs_local = M_local * (L + 1) / 2.0
+    P_local = int(np.unique(prob.obs_point).size)
+    n_expl = sum(s.num_explicit_solves for s in summaries)
+    fused = bool(s_last.explicit_fused)
     kernels = {
         "k_linearize (Jacobian sweep)": dict(ms=sum(s.linearize_ms for s in summaries), n=sum(s.num_linearize for s in summaries),
                                              bytes=(20 + 40 + 96.0 / L) * M_local),
         "k_schur_product (implicit S*p, one per PCG iteration)": dict(ms=sum(s.schur_product_ms for s in summaries),
                                                                       n=sum(s.num_schur_products for s in summaries),
                                                                       bytes=(28 + 72.0 / L) * M_local),
-        "k_schur_w (W = Jc'Jp and W H~ per observation)": dict(ms=sum(s.schur_w_ms for s in summaries),
-                                                              n=sum(s.num_explicit_solves for s in summaries),
-                                                              bytes=(28 + 288 + 120.0 / L) * M_local),
-        "k_schur_pairs (image-pair blocks of the Schur complement)": dict(ms=sum(s.schur_pairs_ms for s in summaries),
-                                                                         n=sum(s.num_explicit_solves for s in summaries),
-                                                                         bytes=288.0 * M_local + 8.0 * pairs_local),
-        "k_schur_assemble + k_chol_blocked (reduced system solve)": dict(ms=sum(s.cholesky_ms for s in summaries),
-                                                                        n=sum(s.num_explicit_solves for s in summaries), bytes=None),
+        "k_schur_assemble + k_chol_blocked (reduced system solve)": dict(ms=sum(s.cholesky_ms for s in summaries), n=n_expl, bytes=None),
     }
+    if fused:
+        # fused tile kernel: D 24 + idx 4 per observation, X/H~/G'E/w^ 120 per point, 4 B per pair entry,
+        # 8 B per (tile, image pair) task; W and W H~ never leave shared memory
+        kernels["k_schur_tile (W, W H~ in shared memory + pair products, fused)"] = dict(
+            ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
+            bytes=28.0 * M_local + 120.0 * P_local + 4.0 * s_last.num_pair_entries + 8.0 * s_last.num_pair_tasks)
+    else:
+        kernels["k_schur_w (W = Jc'Jp and W H~ per observation)"] = dict(ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
+                                                                         bytes=(28 + 288 + 120.0 / L) * M_local)
+        kernels["k_schur_pairs (image-pair blocks of the Schur complement)"] = dict(ms=sum(s.schur_pairs_ms for s in summaries), n=n_expl,
+                                                                                    bytes=288.0 * M_local + 8.0 * pairs_local)
 
     def roof(name):
         k = kernels[name]
@@ -316,7 +323,7 @@ def main():
                                      1: "exact step: explicit Schur complement + banded Cholesky on the device (reference rule for <= 1000 images)"}
                    [s_last.linear_solver_used],
                    "parallelism": f"points sharded over {world} GPU(s); NCCL all-reduce of the camera-side accumulators / reduced system",
-                   "l2": "per-step working set (observations + W arrays, > 2 GB) is larger than the 126 MB L2; no flush needed"},
+                   "l2": "per-step working set (observations, linearisation, pair entries: ~0.7 GB) is larger than the 126 MB L2; no flush needed"},
         "lm_iterations_per_step": iters, "pcg_iterations_per_step": lin_its,
         "obs_iterations_per_sec": M_total * sum(s.num_iterations for s in summaries) / t_total,
         "device_ms_per_step": sum(s.device_ms for s in summaries) / len(summaries),
