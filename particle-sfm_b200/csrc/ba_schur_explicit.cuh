@@ -239,7 +239,7 @@ struct StArgs {
   int intr;
   const unsigned int* entries;   // (li << 16) | lj, tile-local indices, sorted by (tile, a, b)
   const int* task_slot;          // [ntasks] band-block slot a * (span + 1) + (b - a)
-  const int* task_beg;           // [ntasks + 1] entry range of the task
+  const int2* task_rng;          // [ntasks] entry range (begin, end) of the task; tasks of a tile ordered longest first
   const int* tile_task;          // [T + 1] task range of the tile
   double* Sband;                 // [nrep][F * (span + 1) * 36]
   size_t band_stride;
@@ -340,7 +340,7 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     const int t = t0 + (ROT ? (q >> 2) : (q >> 1));
     const int half = ROT ? ((q >> 1) & 1) : 1, par = q & 1;
     int e0 = 0, e1 = 0;
-    if (valid) { e0 = __ldg(a.task_beg + t); e1 = __ldg(a.task_beg + t + 1); }
+    if (valid) { const int2 rg = __ldg(a.task_rng + t); e0 = rg.x; e1 = rg.y; }
     double acc[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) acc[k] = 0.0;
@@ -359,8 +359,8 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
-          acc[6 * r + c] += av[3 * r] * bv[3 * c] + av[3 * r + 1] * bv[3 * c + 1] + av[3 * r + 2] * bv[3 * c + 2];
+        for (int c = 0; c < 6; ++c)   // three chained FMAs per element (no separate product sum)
+          acc[6 * r + c] = fma(av[3 * r + 2], bv[3 * c + 2], fma(av[3 * r + 1], bv[3 * c + 1], fma(av[3 * r], bv[3 * c], acc[6 * r + c])));
     }
 #pragma unroll
     for (int k = 0; k < 18; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
@@ -452,6 +452,23 @@ __global__ void k_pair_fill_tile(const int* pt_ptr, const int* obs_pt, const int
     keys[o] = khi | a;
     vals[o] = ((unsigned)(j - base) << 16) | (unsigned)(k - base);
   }
+}
+
+// tasks of a tile are processed longest first (lanes of a warp then run similar trip counts and
+// the short tasks fill the last pass): sort key (tile, ~count), payload = task index
+__global__ void k_task_sortkeys(const unsigned long long* ukeys, const int* ucount, int ntasks, int fbits,
+                                unsigned long long* key2, int* idx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks) return;
+  key2[t] = ((ukeys[t] >> (2 * fbits)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ucount[t]);
+  idx[t] = t;
+}
+__global__ void k_task_gather(const int* order, const int* slot_in, const int* beg_in, int ntasks, int* slot_out, int2* rng_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks) return;
+  const int o = order[t];
+  slot_out[t] = slot_in[o];
+  rng_out[t] = make_int2(beg_in[o], beg_in[o + 1]);
 }
 
 // task t (one run of equal keys) -> band-block slot; tile -> first task (lower bound)

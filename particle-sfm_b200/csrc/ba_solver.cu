@@ -146,7 +146,8 @@ struct psfm_ba_solver {
   int span = 0, ntasks = 0, band_nrep = 1;
   size_t band_n = 0;
   DBuf<unsigned int> d_tentries;
-  DBuf<int> d_task_slot, d_task_beg, d_tile_task;
+  DBuf<int> d_task_slot, d_tile_task;
+  DBuf<int2> d_task_rng;
   DBuf<double> d_xband, d_bandrep;      // d_xband = [xcam F*NVX2 | Sband band_n] (one all-reduce)
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
@@ -877,15 +878,26 @@ void ensure_pairs(psfm_ba_solver* S) {
     PSFM_CUDA(cudaMemcpyAsync(&nt, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSFM_CUDA(cudaStreamSynchronize(st));
     S->ntasks = nt;
-    S->d_task_slot.alloc(nt, st); S->d_task_beg.alloc((size_t)nt + 1, st); S->d_tile_task.alloc((size_t)T + 1, st);
+    S->d_task_slot.alloc(nt, st); S->d_task_rng.alloc(nt, st); S->d_tile_task.alloc((size_t)T + 1, st);
+    DBuf<int> slot0, beg0, idx0, order;
+    DBuf<unsigned long long> key2, key2_out;
+    slot0.alloc(nt, st); beg0.alloc((size_t)nt + 1, st); idx0.alloc(nt, st); order.alloc(nt, st); key2.alloc(nt, st); key2_out.alloc(nt, st);
     PSFM_CUDA(cudaMemsetAsync(ucount.p + nt, 0, sizeof(int), st));
     {
       size_t need = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, need, ucount.p, S->d_task_beg.p, nt + 1, st);
+      cub::DeviceScan::ExclusiveSum(nullptr, need, ucount.p, beg0.p, nt + 1, st);
       DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
-      cub::DeviceScan::ExclusiveSum(tmp.p, need, ucount.p, S->d_task_beg.p, nt + 1, st);
+      cub::DeviceScan::ExclusiveSum(tmp.p, need, ucount.p, beg0.p, nt + 1, st);
     }
-    if (nt) { k_task_slots<<<grid_for(nt), 256, 0, st>>>(uk64.p, nt, fb, S->span, S->d_task_slot.p); PSFM_LAUNCH_CHECK(); }
+    if (nt) {
+      k_task_slots<<<grid_for(nt), 256, 0, st>>>(uk64.p, nt, fb, S->span, slot0.p); PSFM_LAUNCH_CHECK();
+      k_task_sortkeys<<<grid_for(nt), 256, 0, st>>>(uk64.p, ucount.p, nt, fb, key2.p, idx0.p); PSFM_LAUNCH_CHECK();
+      size_t need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, key2.p, key2_out.p, idx0.p, order.p, nt, 0, 32 + tb, st);
+      DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
+      cub::DeviceRadixSort::SortPairs(tmp.p, need, key2.p, key2_out.p, idx0.p, order.p, nt, 0, 32 + tb, st);
+      k_task_gather<<<grid_for(nt), 256, 0, st>>>(order.p, slot0.p, beg0.p, nt, S->d_task_slot.p, S->d_task_rng.p); PSFM_LAUNCH_CHECK();
+    }
     k_tile_tasks<<<grid_for((size_t)T + 1), 256, 0, st>>>(uk64.p, nt, fb, T, S->d_tile_task.p);
     PSFM_LAUNCH_CHECK();
     S->band_n = (size_t)F * (S->span + 1) * 36;
@@ -1000,7 +1012,7 @@ bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
   StArgs w;
   w.L = lin_of(S); w.pose16 = S->d_pose16.p; w.X = S->d_X[S->cur].p; w.ht = S->d_hinv.p; w.wt = S->d_w.p; w.wk = S->d_wk.p;
   w.K = S->d_K[S->cur].p; w.acc_cam = S->d_xcamrep.p; w.rep_stride = nx; w.intr = c.intr;
-  w.entries = S->d_tentries.p; w.task_slot = S->d_task_slot.p; w.task_beg = S->d_task_beg.p; w.tile_task = S->d_tile_task.p;
+  w.entries = S->d_tentries.p; w.task_slot = S->d_task_slot.p; w.task_rng = S->d_task_rng.p; w.tile_task = S->d_tile_task.p;
   w.Sband = S->d_bandrep.p; w.band_stride = S->band_n; w.nrep_mask = S->band_nrep - 1;
   auto mark = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, bool begin) {
     cudaEvent_t e = S->events.get();
