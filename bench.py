@@ -56,20 +56,34 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def _lines(self):
+        try:
+            with open(self.f.name) as g:
+                return g.read().splitlines()
+        except OSError:
+            return []
+
+    def begin(self):
+        """Call when the timed region starts: only later samples are reported (the sampler is
+        started before the warm-up so that nvidia-smi's start-up is not inside the region)."""
+        self.first = len(self._lines())
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
-        self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        lines = self._lines()
+        first = min(getattr(self, "first", 0), max(0, len(lines) - 1))
+        for line in lines[first:]:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 7:
                 continue
@@ -143,7 +157,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=WORKLOAD["num_points"], help="trajectories of the BA workload")
@@ -210,10 +224,12 @@ def main():
         S.set_state(*init)
         return S.run(o)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.begin()
     launches0 = lib.psfm_launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -264,13 +280,22 @@ def main():
         kernels["k_schur_pairs (image-pair blocks of the Schur complement)"] = dict(ms=sum(s.schur_pairs_ms for s in summaries), n=n_expl,
                                                                                     bytes=288.0 * M_local + 8.0 * pairs_local)
 
+    # measured DRAM traffic per launch (ncu --set full capture of this workload at 1 GPU)
+    traffic = {}
+    try:
+        if world == 1 and args.points == WORKLOAD["num_points"]:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")) as f:
+                traffic = json.load(f)
+    except (OSError, ValueError):
+        traffic = {}
+
     def roof(name):
         k = kernels[name]
         if k["n"] == 0 or k["ms"] <= 0:
             return None
         avg = k["ms"] / k["n"]
         d = {"kernel": name, "bound": "hbm", "avg_launch_ms": avg, "launches": k["n"], "share_of_step": k["ms"] / (1e3 * t_local),
-             "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None}
+             "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": traffic.get(name.split(" ")[0])}
         if k["bytes"]:
             d["algorithmic_bytes_per_launch"] = k["bytes"]
             d["achieved"] = k["bytes"] / (avg * 1e-3) / 1e9

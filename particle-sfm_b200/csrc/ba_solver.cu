@@ -901,7 +901,7 @@ void ensure_pairs(psfm_ba_solver* S) {
     k_tile_tasks<<<grid_for((size_t)T + 1), 256, 0, st>>>(uk64.p, nt, fb, T, S->d_tile_task.p);
     PSFM_LAUNCH_CHECK();
     S->band_n = (size_t)F * (S->span + 1) * 36;
-    int nrep = NREP;
+    int nrep = 8;   // the pair-task REDs are spread over many band blocks: few replicas suffice (fold cost grows with them)
     while (nrep > 1 && S->band_n * nrep * sizeof(double) > ((size_t)256 << 20)) nrep >>= 1;
     S->band_nrep = nrep;
     S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
