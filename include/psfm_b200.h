@@ -253,6 +253,9 @@ int psfm_ba_create(const psfm_ba_problem* problem, psfm_ba_solver** out);
 int psfm_ba_set_state(psfm_ba_solver* s, const double* qvec, const double* tvec,
                       const double* xyz, const double* cam_params);
 int psfm_ba_run(psfm_ba_solver* s, const psfm_ba_options* opts, psfm_ba_summary* summary);
+/* Writes the state back (any pointer may be NULL).  xyz: only the points this solver observes
+   are written (Ceres never touches a Point3D without a residual either); on a shard of a
+   multi-GPU problem those are the shard's own points. */
 int psfm_ba_get_state(psfm_ba_solver* s, double* qvec, double* tvec, double* xyz,
                       double* cam_params);
 void psfm_ba_destroy(psfm_ba_solver* s);

@@ -57,20 +57,6 @@ __global__ void k_fold_replicas(double* dst, double* rep, size_t n, size_t strid
   dst[i] = scale ? scale[i] * s : s;
 }
 
-// points between the caller's order and the tile order
-__global__ void k_gather_points(const double* __restrict__ full, const int* __restrict__ orig, int P, double* __restrict__ X) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const size_t o = 3 * (size_t)orig[p];
-  X[3 * (size_t)p] = full[o]; X[3 * (size_t)p + 1] = full[o + 1]; X[3 * (size_t)p + 2] = full[o + 2];
-}
-__global__ void k_scatter_points(const double* __restrict__ X, const int* __restrict__ orig, int P, double* __restrict__ full) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const size_t o = 3 * (size_t)orig[p];
-  full[o] = X[3 * (size_t)p]; full[o + 1] = X[3 * (size_t)p + 1]; full[o + 2] = X[3 * (size_t)p + 2];
-}
-
 // xs = s o x  (the tile kernels work with the unscaled Jacobian: J_scaled x = J (s o x))
 __global__ void k_scale_vec(const double* x, const double* scale, size_t n, double* xs, const int* skip_flag) {
   if (skip_flag && *skip_flag != 0) return;

@@ -107,11 +107,7 @@ struct psfm_ba_solver {
   std::vector<int> image_camera;
   std::vector<unsigned char> pose_constant, tvec_mask, camera_constant, img_has_obs, cam_has_obs;
   // host state (caller layout)
-  std::vector<double> h_qvec, h_tvec, h_K;
-  double* h_xyz = nullptr;          // pinned, caller layout [3 * P_total]; permuted to / from tile order on the device
-  size_t h_xyz_bytes = 0;
-  DBuf<double> d_xyz_full;          // [3 * P_total] caller layout
-  DBuf<int> d_pt_orig;              // [P] internal point -> caller's point id
+  std::vector<double> h_qvec, h_tvec, h_K;   // the points' state of record is pin_state's X part (tile order, own points only)
   // device structure
   DBuf<int> d_tile_start, d_tile_pt, d_pt_ptr, d_obs_img, d_obs_pt, d_cseg_ptr, d_cseg_img, d_img_cam;
   DBuf<unsigned short> d_tile_perm, d_cseg_off, d_obs_lseg, d_obs_lpt;
@@ -170,7 +166,6 @@ struct psfm_ba_solver {
   ~psfm_ba_solver() {
     if (stream) cudaStreamSynchronize(stream);
     g_pinned.release(hs, hs_bytes);
-    g_pinned.release(h_xyz, h_xyz_bytes);
     g_pinned.release(pin_state, pin_state_bytes);
   }
 };
@@ -383,10 +378,7 @@ void alloc_work(psfm_ba_solver* S) {
   S->d_pcg.alloc(1, S->stream);
   S->hs = (HostScalars*)g_pinned.acquire(sizeof(HostScalars), &S->hs_bytes);
   S->pin_state = (double*)g_pinned.acquire(sizeof(double) * (8 * F + 3 * P + 3 * C + 1), &S->pin_state_bytes);
-  S->h_xyz = (double*)g_pinned.acquire(sizeof(double) * (3 * (size_t)S->P_total + 1), &S->h_xyz_bytes);
-  S->d_xyz_full.alloc(3 * (size_t)S->P_total, S->stream);
-  S->d_pt_orig.alloc(P, S->stream); S->d_pt_orig.upload(S->pt_orig.data(), P, S->stream);
-  if (!S->hs || !S->pin_state || !S->h_xyz) { set_error("cudaMallocHost failed"); throw CudaFail{PSFM_ERR_CUDA}; }
+  if (!S->hs || !S->pin_state) { set_error("cudaMallocHost failed"); throw CudaFail{PSFM_ERR_CUDA}; }
   memset(S->hs, 0, sizeof(HostScalars));
 }
 
@@ -491,6 +483,24 @@ int resolve_cfg(psfm_ba_solver* S, const psfm_ba_options* opts, RunCfg& c) {
   return PSFM_OK;
 }
 
+// caller's xyz [3 * P_total] <-> the pinned X staging (tile order, this solver's observed points)
+void gather_points(psfm_ba_solver* S, const double* xyz) {
+  double* X = S->pin_state + 8 * (size_t)S->F;
+  const int* po = S->pt_orig.data();
+  for (int id = 0; id < S->P; ++id) {
+    const double* src = xyz + 3 * (size_t)po[id];
+    X[3 * (size_t)id] = src[0]; X[3 * (size_t)id + 1] = src[1]; X[3 * (size_t)id + 2] = src[2];
+  }
+}
+void scatter_points(const psfm_ba_solver* S, double* xyz) {
+  const double* X = S->pin_state + 8 * (size_t)S->F;
+  const int* po = S->pt_orig.data();
+  for (int id = 0; id < S->P; ++id) {
+    double* dst = xyz + 3 * (size_t)po[id];
+    dst[0] = X[3 * (size_t)id]; dst[1] = X[3 * (size_t)id + 1]; dst[2] = X[3 * (size_t)id + 2];
+  }
+}
+
 void upload_state(psfm_ba_solver* S) {
   const int F = S->F, P = S->P, C = S->C;
   double* pose = S->pin_state;
@@ -506,12 +516,10 @@ void upload_state(psfm_ba_solver* S) {
     for (int k = 0; k < 3; ++k) pose[8 * (size_t)i + 4 + k] = S->h_tvec[3 * (size_t)i + k];
     pose[8 * (size_t)i + 7] = 0.0;
   }
-  (void)X;
   for (int k = 0; k < 3 * C; ++k) K[k] = S->h_K[k];
   S->cur = 0;
   S->d_pose[0].upload(pose, 8 * (size_t)F, S->stream);
-  S->d_xyz_full.upload(S->h_xyz, 3 * (size_t)S->P_total, S->stream);
-  if (P) { k_gather_points<<<grid_for(P), 256, 0, S->stream>>>(S->d_xyz_full.p, S->d_pt_orig.p, P, S->d_X[0].p); PSFM_LAUNCH_CHECK(); }
+  S->d_X[0].upload(X, 3 * (size_t)P, S->stream);
   S->d_K[0].upload(K, 3 * (size_t)C, S->stream);
   PSFM_CUDA(cudaStreamSynchronize(S->stream));
 }
@@ -521,12 +529,8 @@ void download_state(psfm_ba_solver* S) {
   double* pose = S->pin_state;
   double* X = pose + 8 * (size_t)F;
   double* K = X + 3 * (size_t)P;
-  (void)X;
   PSFM_CUDA(cudaMemcpyAsync(pose, S->d_pose[S->cur].p, 8 * (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
-  if (P) {
-    k_scatter_points<<<grid_for(P), 256, 0, S->stream>>>(S->d_X[S->cur].p, S->d_pt_orig.p, P, S->d_xyz_full.p); PSFM_LAUNCH_CHECK();
-    PSFM_CUDA(cudaMemcpyAsync(S->h_xyz, S->d_xyz_full.p, 3 * (size_t)S->P_total * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
-  }
+  if (P) PSFM_CUDA(cudaMemcpyAsync(X, S->d_X[S->cur].p, 3 * (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
   PSFM_CUDA(cudaMemcpyAsync(K, S->d_K[S->cur].p, 3 * (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
   PSFM_CUDA(cudaStreamSynchronize(S->stream));
   for (int k = 0; k < 3 * C; ++k) S->h_K[k] = K[k];
@@ -1381,7 +1385,7 @@ extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
     S->h_K.assign(pb->cam_params, pb->cam_params + 3 * (size_t)S->C);
     PhaseTimer tm;
     alloc_work(S);
-    memcpy(S->h_xyz, pb->xyz, sizeof(double) * 3 * (size_t)S->P_total);
+    gather_points(S, pb->xyz);
     PSFM_CUDA(cudaStreamSynchronize(S->stream));
     tm.mark("allocate work buffers");
   } catch (const CudaFail& f) {
@@ -1397,7 +1401,7 @@ extern "C" int psfm_ba_set_state(psfm_ba_solver* S, const double* qvec, const do
   if (!S) return PSFM_ERR_INVALID;
   if (qvec) S->h_qvec.assign(qvec, qvec + 4 * (size_t)S->F);
   if (tvec) S->h_tvec.assign(tvec, tvec + 3 * (size_t)S->F);
-  if (xyz) memcpy(S->h_xyz, xyz, sizeof(double) * 3 * (size_t)S->P_total);
+  if (xyz) gather_points(S, xyz);
   if (cam_params) S->h_K.assign(cam_params, cam_params + 3 * (size_t)S->C);
   return PSFM_OK;
 }
@@ -1406,7 +1410,7 @@ extern "C" int psfm_ba_get_state(psfm_ba_solver* S, double* qvec, double* tvec, 
   if (!S) return PSFM_ERR_INVALID;
   if (qvec) memcpy(qvec, S->h_qvec.data(), sizeof(double) * S->h_qvec.size());
   if (tvec) memcpy(tvec, S->h_tvec.data(), sizeof(double) * S->h_tvec.size());
-  if (xyz) memcpy(xyz, S->h_xyz, sizeof(double) * 3 * (size_t)S->P_total);
+  if (xyz) scatter_points(S, xyz);   // points this solver does not observe are left untouched
   if (cam_params) memcpy(cam_params, S->h_K.data(), sizeof(double) * S->h_K.size());
   return PSFM_OK;
 }
