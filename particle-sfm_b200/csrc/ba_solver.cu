@@ -272,8 +272,10 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   for (int j = 0; j < P; ++j) maxL = std::max(maxL, h_cs[j]);
   S->P = P; S->maxL = maxL;
   S->pt_orig.assign(h_order.begin(), h_order.begin() + P);
-  if (maxL > 1024) { set_error("a track with more than 1024 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
-  S->tile = maxL <= 256 ? 256 : (maxL <= 512 ? 512 : 1024);
+  // A track lives in one tile and a tile's per-image staging grows with the images it spans: beyond
+  // 512 observations the shared memory of an SM (227 KB) no longer holds a tile.
+  if (maxL > 512) { set_error("a track with more than 512 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
+  S->tile = maxL <= 256 ? 256 : 512;
   // tiles: whole points, <= tile observations (greedy, host: P iterations)
   const int TILE = S->tile;
   std::vector<int> pt_ptr(P + 1, 0), tile_start, tile_pt;
@@ -312,8 +314,7 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   PSFM_CUDA(cudaMemsetAsync(tile_ns.p, 0, sizeof(int) * ((size_t)T + 1), st));
   if (T) {
     if (TILE == 256) k_st_tile_order<256><<<T, 256, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
-    else if (TILE == 512) k_st_tile_order<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
-    else k_st_tile_order<1024><<<T, 1024, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
+    else k_st_tile_order<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_obs_img.p, S->d_obs_pt.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_obs_lpt.p, tile_ns.p);
     PSFM_LAUNCH_CHECK();
   }
   {
@@ -335,8 +336,7 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   S->d_cseg_img.alloc(S->nseg, st); S->d_cseg_off.alloc(S->nseg, st);
   if (T) {
     if (TILE == 256) k_st_tile_segments<256><<<T, 256, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
-    else if (TILE == 512) k_st_tile_segments<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
-    else k_st_tile_segments<1024><<<T, 1024, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
+    else k_st_tile_segments<512><<<T, 512, 0, st>>>(S->d_tile_start.p, S->d_obs_img.p, S->d_tile_perm.p, S->d_obs_lseg.p, S->d_cseg_ptr.p, S->d_cseg_img.p, S->d_cseg_off.p);
     PSFM_LAUNCH_CHECK();
   }
   // pipeline form: packed tile headers, tile-relative point starts, 32-bit segment offsets
@@ -402,8 +402,7 @@ void alloc_work(psfm_ba_solver* S) {
       };                                                                                                   \
       using std::integral_constant;                                                                        \
       if ((S)->tile == 256) { if (ROT) _go(integral_constant<int, 256>{}, std::true_type{}); else _go(integral_constant<int, 256>{}, std::false_type{}); } \
-      else if ((S)->tile == 512) { if (ROT) _go(integral_constant<int, 512>{}, std::true_type{}); else _go(integral_constant<int, 512>{}, std::false_type{}); } \
-      else { if (ROT) _go(integral_constant<int, 1024>{}, std::true_type{}); else _go(integral_constant<int, 1024>{}, std::false_type{}); } \
+      else { if (ROT) _go(integral_constant<int, 512>{}, std::true_type{}); else _go(integral_constant<int, 512>{}, std::false_type{}); } \
       PSFM_LAUNCH_CHECK();                                                                                 \
     }                                                                                                      \
   } while (0)
@@ -566,7 +565,7 @@ PipeSrc pipe_src(psfm_ba_solver* S) {
 }
 
 // the pipelined kernels need the tile inputs to fit twice in shared memory
-bool pipe_ok(psfm_ba_solver* S, size_t smem) { return S->pipe && S->tile <= 512 && smem <= (size_t)227 * 1024; }
+bool pipe_ok(psfm_ba_solver* S, size_t smem) { return S->pipe && smem <= (size_t)227 * 1024; }
 
 // Jacobian sweep at the current state (r, J, E'E, E'r, F'F blocks, F'r, cost)
 void do_linearize(psfm_ba_solver* S, const RunCfg& c, bool timed) {
@@ -851,7 +850,7 @@ void ensure_pairs(psfm_ba_solver* S) {
   {
     const size_t smem256 = TileSmem<256>::bytes(WW, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(WW, 15, S->cap_ns, S->cap_np);
     const size_t smem = S->tile == 256 ? smem256 : smem512;
-    S->fused = S->tile <= 512 && smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
+    S->fused = smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
   }
   if (S->fused) {
     // ---- tile-local tasks for k_schur_tile

@@ -119,7 +119,7 @@ def test_zero_noise_recovers_truth(gpu):
 
 
 def test_long_tracks_and_unobserved_points(gpu):
-    # tracks longer than 256 observations select the 512/1024-wide tiles; points without
+    # tracks longer than 256 observations select the 512-wide tiles; points without
     # observations and images without observations are left untouched
     prob, _ = syn.make_ba_problem(300, 40, 300, seed=10)
     prob2, _ = syn.make_ba_problem(300, 400, 9, seed=11)
@@ -202,3 +202,60 @@ def test_exact_mode_principal_point_falls_back_to_tight_pcg(gpu):
     assert s1.num_explicit_solves == 0 and s1.num_schur_products > 0
     assert s1.num_iterations == s0.num_iterations
     assert abs(s1.final_cost - s0.final_cost) <= 1e-6 * s0.final_cost
+
+
+def _mixed_track_problem(frames, long_len, seed):
+    """A few tracks of `long_len` observations (select the 512-wide tiles) plus short ones."""
+    a, _ = syn.make_ba_problem(frames, 24, long_len, seed=seed)
+    b, _ = syn.make_ba_problem(frames, 600, 8, seed=seed + 1)
+    return _abi.BAProblem(a.qvec, a.tvec, np.concatenate([a.xyz, b.xyz]), a.cam_params,
+                          np.concatenate([a.obs_image, b.obs_image]),
+                          np.concatenate([a.obs_point, b.obs_point + a.num_points]),
+                          np.concatenate([a.obs_xy, b.obs_xy]), a.image_camera,
+                          a.pose_constant, a.tvec_constant_mask, a.camera_constant)
+
+
+@pytest.mark.parametrize("frames,long_len,fused", [(320, 300, 1), (520, 500, 0)])
+def test_exact_mode_wide_tiles(gpu, frames, long_len, fused):
+    """Tracks of 300 observations run the fused Schur kernel on 512-wide tiles; with tracks of
+    500 observations over 520 images the W buffer plus the per-image staging exceed the shared
+    memory of an SM and the unfused k_schur_w + k_schur_pairs path takes over.  Both must
+    reproduce the oracle's exact step."""
+    p = _mixed_track_problem(frames, long_len, seed=30)
+    o = _opts(True, True, _abi.SOLVER_EXACT_SCHUR)
+    o.max_num_iterations = 3
+    p0, p1 = p.copy(), p.copy()
+    s0 = oracle.ba_solve(p0, o)
+    s1 = ba.solve_problem(p1, o)
+    assert s1.explicit_fused == fused and s1.num_pair_entries > 0
+    assert s1.num_iterations == s0.num_iterations
+    assert abs(s1.initial_cost - s0.initial_cost) <= 1e-10 * s0.initial_cost
+    assert abs(s1.final_cost - s0.final_cost) <= 1e-8 * s0.final_cost
+    assert _rel(p1.tvec, p0.tvec) < 1e-7 and _rel(p1.xyz, p0.xyz) < 1e-7
+
+
+def test_code_paths_agree(gpu, monkeypatch):
+    """The persistent cp.async-pipelined kernels, the one-CTA-per-tile kernels, the fused and
+    the unfused Schur paths and both Cholesky dispatches are the same arithmetic in a different
+    schedule: identical LM trajectories, parameters equal to ~1e-12."""
+    prob, _ = syn.make_ba_problem(40, 6000, 9, seed=31, dynamic_fraction=0.1)
+    o = _opts(True, True, _abi.SOLVER_EXACT_SCHUR)
+    ref = prob.copy()
+    s_ref = ba.solve_problem(ref, o)
+    assert s_ref.explicit_fused == 1
+    for env in ("PSFM_NO_PIPE", "PSFM_SCHUR_UNFUSED", "PSFM_NO_PIPE_SCHUR"):
+        monkeypatch.setenv(env, "1")
+        p = prob.copy()
+        s = ba.solve_problem(p, o)
+        monkeypatch.delenv(env)
+        assert s.num_iterations == s_ref.num_iterations and s.termination == s_ref.termination, env
+        assert abs(s.final_cost - s_ref.final_cost) <= 1e-11 * s_ref.final_cost, env
+        assert _rel(p.xyz, ref.xyz) < 1e-9 and _rel(p.qvec, ref.qvec) < 1e-9, env
+        if env == "PSFM_SCHUR_UNFUSED":
+            assert s.explicit_fused == 0
+
+
+def test_tracks_longer_than_a_tile_are_rejected(gpu):
+    p = _mixed_track_problem(620, 600, seed=32)
+    with pytest.raises(Exception, match="512 observations"):
+        ba.solve_problem(p, _opts(True, True, _abi.SOLVER_AUTO))
