@@ -92,12 +92,16 @@ __device__ __forceinline__ void loss_eval(const LossP l, const double s, double&
 // ------------------------------------------------------------------ tile plumbing
 
 // Shared memory of a tile kernel (all SoA so that lanes of one point / one image broadcast):
-//   sv   [NV][TILE]      per-observation values being reduced
+//   sv   [NV][TILE + 1]  per-observation values being reduced (row stride PSFM_SVS)
 //   sw   [4][cap_np]     per-point scratch
 //   sred [9*32]          block-reduction scratch
 //   simg [12][cap_ns]    per image segment: R (row-major 9), t (3)
 //   sx   [6][cap_ns]     per image segment: scaled input vector (rot 3 | t 3)
 //   spt  [NPT][cap_np]   per point: X (3) [, H~ (6) [, w^ or G'E focal row (3) [, w^ (3)]]]
+// Row stride of sv: TILE + 1 so that lanes working on different components k of the same
+// observation column hit different banks (the reductions below run component-fastest).
+#define PSFM_SVS (TILE + 1)
+
 template <int TILE>
 struct TileSmem {
   double *sv, *sw, *sred, *simg, *sx, *spt;
@@ -105,13 +109,13 @@ struct TileSmem {
   unsigned short* perm;
   int cap_ns, cap_np;
   static size_t bytes(int nv, int npt, int cap_ns, int cap_np) {
-    return sizeof(double) * ((size_t)nv * TILE + 4 * (size_t)cap_np + 9 * 32 + 18 * (size_t)cap_ns + (size_t)npt * cap_np) +
+    return sizeof(double) * ((size_t)nv * PSFM_SVS + 4 * (size_t)cap_np + 9 * 32 + 18 * (size_t)cap_ns + (size_t)npt * cap_np) +
            sizeof(int) * ((size_t)cap_np + 2 * (size_t)cap_ns + 4) + sizeof(unsigned short) * (size_t)TILE + 32;
   }
   __device__ __forceinline__ void carve(unsigned char* base, int nv, int npt, int cns, int cnp) {
     cap_ns = cns; cap_np = cnp;
     sv = reinterpret_cast<double*>(base);
-    sw = sv + (size_t)nv * TILE;
+    sw = sv + (size_t)nv * PSFM_SVS;
     sred = sw + 4 * (size_t)cnp;
     simg = sred + 9 * 32;
     sx = simg + 12 * (size_t)cns;
@@ -221,8 +225,8 @@ __device__ __forceinline__ double block_sum_multi(const double (&v)[N], double* 
 template <int TILE, typename Fn>
 __device__ __forceinline__ void tile_reduce_points(const TileSmem<TILE>& sm, const TileInfo& ti, int nv, Fn fn) {
   for (int pair = threadIdx.x; pair < nv * ti.np; pair += TILE) {
-    const int k = pair / ti.np, l = pair - k * ti.np;
-    const double* row = sm.sv + k * TILE;
+    const int l = pair / nv, k = pair - l * nv;       // component fastest: conflict-free rows, see PSFM_SVS
+    const double* row = sm.sv + k * PSFM_SVS;
     double acc = 0.0;
     for (int e = sm.pstart[l]; e < sm.pstart[l + 1]; ++e) acc += row[e];
     fn(k, l, acc);
@@ -233,8 +237,8 @@ __device__ __forceinline__ void tile_reduce_points(const TileSmem<TILE>& sm, con
 template <int TILE, typename Fn>
 __device__ __forceinline__ void tile_reduce_images(const TileSmem<TILE>& sm, const TileInfo& ti, int nv, Fn fn) {
   for (int pair = threadIdx.x; pair < nv * ti.ns; pair += TILE) {
-    const int k = pair / ti.ns, s = pair - k * ti.ns;
-    const double* row = sm.sv + k * TILE;
+    const int s = pair / nv, k = pair - s * nv;       // component fastest; perm[e] is a broadcast
+    const double* row = sm.sv + k * PSFM_SVS;
     double acc = 0.0;
     for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
     fn(k, sm.cimg[s], acc);
@@ -358,22 +362,22 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
   const int nvp = 9 + 3 * a.intr;
   {
     double* sv = sm.sv + tid;
-    sv[0 * TILE] = jp0[0] * jp0[0] + jp1[0] * jp1[0];
-    sv[1 * TILE] = jp0[0] * jp0[1] + jp1[0] * jp1[1];
-    sv[2 * TILE] = jp0[0] * jp0[2] + jp1[0] * jp1[2];
-    sv[3 * TILE] = jp0[1] * jp0[1] + jp1[1] * jp1[1];
-    sv[4 * TILE] = jp0[1] * jp0[2] + jp1[1] * jp1[2];
-    sv[5 * TILE] = jp0[2] * jp0[2] + jp1[2] * jp1[2];
+    sv[0 * PSFM_SVS] = jp0[0] * jp0[0] + jp1[0] * jp1[0];
+    sv[1 * PSFM_SVS] = jp0[0] * jp0[1] + jp1[0] * jp1[1];
+    sv[2 * PSFM_SVS] = jp0[0] * jp0[2] + jp1[0] * jp1[2];
+    sv[3 * PSFM_SVS] = jp0[1] * jp0[1] + jp1[1] * jp1[1];
+    sv[4 * PSFM_SVS] = jp0[1] * jp0[2] + jp1[1] * jp1[2];
+    sv[5 * PSFM_SVS] = jp0[2] * jp0[2] + jp1[2] * jp1[2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sv[(6 + k) * TILE] = jp0[k] * r0 + jp1[k] * r1;
+    for (int k = 0; k < 3; ++k) sv[(6 + k) * PSFM_SVS] = jp0[k] * r0 + jp1[k] * r1;
     if (a.intr >= 1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) sv[(9 + k) * TILE] = jf0 * jp0[k] + jf1 * jp1[k];
+      for (int k = 0; k < 3; ++k) sv[(9 + k) * PSFM_SVS] = jf0 * jp0[k] + jf1 * jp1[k];
       if (a.intr == 3) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          sv[(12 + k) * TILE] = sq * jp0[k];
-          sv[(15 + k) * TILE] = sq * jp1[k];
+          sv[(12 + k) * PSFM_SVS] = sq * jp0[k];
+          sv[(15 + k) * PSFM_SVS] = sq * jp1[k];
         }
       }
     }
@@ -393,25 +397,25 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
     if (ROT) {
       const double jr00 = 2.0 * a02 * g.w[1], jr01 = 2.0 * (a00 * g.w[2] - a02 * g.w[0]), jr02 = -2.0 * a00 * g.w[1];
       const double jr10 = 2.0 * (a12 * g.w[1] - a00 * g.w[2]), jr11 = -2.0 * a12 * g.w[0], jr12 = 2.0 * a00 * g.w[0];
-      sv[0 * TILE] = jr00 * jr00 + jr10 * jr10;
-      sv[1 * TILE] = jr00 * jr01 + jr10 * jr11;
-      sv[2 * TILE] = jr00 * jr02 + jr10 * jr12;
-      sv[3 * TILE] = jr01 * jr01 + jr11 * jr11;
-      sv[4 * TILE] = jr01 * jr02 + jr11 * jr12;
-      sv[5 * TILE] = jr02 * jr02 + jr12 * jr12;
-      sv[12 * TILE] = jr00 * r0 + jr10 * r1;
-      sv[13 * TILE] = jr01 * r0 + jr11 * r1;
-      sv[14 * TILE] = jr02 * r0 + jr12 * r1;
+      sv[0 * PSFM_SVS] = jr00 * jr00 + jr10 * jr10;
+      sv[1 * PSFM_SVS] = jr00 * jr01 + jr10 * jr11;
+      sv[2 * PSFM_SVS] = jr00 * jr02 + jr10 * jr12;
+      sv[3 * PSFM_SVS] = jr01 * jr01 + jr11 * jr11;
+      sv[4 * PSFM_SVS] = jr01 * jr02 + jr11 * jr12;
+      sv[5 * PSFM_SVS] = jr02 * jr02 + jr12 * jr12;
+      sv[12 * PSFM_SVS] = jr00 * r0 + jr10 * r1;
+      sv[13 * PSFM_SVS] = jr01 * r0 + jr11 * r1;
+      sv[14 * PSFM_SVS] = jr02 * r0 + jr12 * r1;
     }
-    sv[6 * TILE] = a00 * a00;
-    sv[7 * TILE] = 0.0;
-    sv[8 * TILE] = a00 * a02;
-    sv[9 * TILE] = a00 * a00;
-    sv[10 * TILE] = a00 * a12;
-    sv[11 * TILE] = a02 * a02 + a12 * a12;
-    sv[15 * TILE] = a00 * r0;
-    sv[16 * TILE] = a00 * r1;
-    sv[17 * TILE] = a02 * r0 + a12 * r1;
+    sv[6 * PSFM_SVS] = a00 * a00;
+    sv[7 * PSFM_SVS] = 0.0;
+    sv[8 * PSFM_SVS] = a00 * a02;
+    sv[9 * PSFM_SVS] = a00 * a00;
+    sv[10 * PSFM_SVS] = a00 * a12;
+    sv[11 * PSFM_SVS] = a02 * a02 + a12 * a12;
+    sv[15 * PSFM_SVS] = a00 * r0;
+    sv[16 * PSFM_SVS] = a00 * r1;
+    sv[17 * PSFM_SVS] = a02 * r0 + a12 * r1;
   }
   __syncthreads();
   {
@@ -419,11 +423,11 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
     double* dst = a.acc_cam + (size_t)(rep & (NREP - 1)) * a.rep_stride;
     const int nvc = ROT ? 18 : 9;
     for (int pair = tid; pair < nvc * ti.ns; pair += TILE) {
-      int k = pair / ti.ns;
-      const int s = pair - k * ti.ns;
+      const int s = pair / nvc;
+      int k = pair - s * nvc;
       if (!ROT) k = (k < 6) ? k + 6 : k + 9;
       if (k == 7) continue;
-      const double* row = sm.sv + k * TILE;
+      const double* row = sm.sv + k * PSFM_SVS;
       double acc = 0.0;
       for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
       atomicAdd(dst + (size_t)sm.cimg[s] * NVL + k, acc);
@@ -635,19 +639,19 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
 #pragma unroll
       for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int k = j; k < 3; ++k) { sv[c * TILE] = -(WH[j][0] * W[k][0] + WH[j][1] * W[k][1] + WH[j][2] * W[k][2]); ++c; }
+        for (int k = j; k < 3; ++k) { sv[c * PSFM_SVS] = -(WH[j][0] * W[k][0] + WH[j][1] * W[k][1] + WH[j][2] * W[k][2]); ++c; }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) sv[(12 + 3 * b + j) * TILE] = -(W[j][0] * w[0] + W[j][1] * w[1] + W[j][2] * w[2]);
+      for (int j = 0; j < 3; ++j) sv[(12 + 3 * b + j) * PSFM_SVS] = -(W[j][0] * w[0] + W[j][1] * w[1] + W[j][2] * w[2]);
     }
   }
   __syncthreads();
   double* dst = a.acc_cam + (size_t)(blockIdx.x & (NREP - 1)) * a.rep_stride;
   const int nvc = ROT ? 18 : 9;
   for (int pair = tid; pair < nvc * ti.ns; pair += TILE) {
-    int k = pair / ti.ns;
-    const int s = pair - k * ti.ns;
+    const int s = pair / nvc;
+    int k = pair - s * nvc;
     if (!ROT) k = (k < 6) ? k + 6 : k + 9;
-    const double* row = sm.sv + k * TILE;
+    const double* row = sm.sv + k * PSFM_SVS;
     double acc = 0.0;
     for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
     atomicAdd(dst + (size_t)sm.cimg[s] * NVL + k, acc);
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schu
     // E'u = R'(D'u)
     const double d0 = a00 * u0, d1 = a00 * u1, d2 = a02 * u0 + a12 * u1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sv[k * TILE] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
+    for (int k = 0; k < 3; ++k) sv[k * PSFM_SVS] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
   }
   __syncthreads();
   const int cnp = sm.cap_np;
@@ -742,12 +746,12 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schu
     // F'v: e = D'v ; rot = 2 w x e ; t = e
     const double e0 = a00 * v0, e1 = a00 * v1, e2 = a02 * v0 + a12 * v1;
     if (ROT) {
-      sv[0 * TILE] = 2.0 * (g.w[1] * e2 - g.w[2] * e1);
-      sv[1 * TILE] = 2.0 * (g.w[2] * e0 - g.w[0] * e2);
-      sv[2 * TILE] = 2.0 * (g.w[0] * e1 - g.w[1] * e0);
-      sv[3 * TILE] = e0; sv[4 * TILE] = e1; sv[5 * TILE] = e2;
+      sv[0 * PSFM_SVS] = 2.0 * (g.w[1] * e2 - g.w[2] * e1);
+      sv[1 * PSFM_SVS] = 2.0 * (g.w[2] * e0 - g.w[0] * e2);
+      sv[2 * PSFM_SVS] = 2.0 * (g.w[0] * e1 - g.w[1] * e0);
+      sv[3 * PSFM_SVS] = e0; sv[4 * PSFM_SVS] = e1; sv[5 * PSFM_SVS] = e2;
     } else {
-      sv[0 * TILE] = e0; sv[1 * TILE] = e1; sv[2 * TILE] = e2;
+      sv[0 * PSFM_SVS] = e0; sv[1 * PSFM_SVS] = e1; sv[2 * PSFM_SVS] = e2;
     }
   }
   __syncthreads();
@@ -820,7 +824,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute
   {
     const double d0 = a00 * u0, d1 = a00 * u1, d2 = a02 * u0 + a12 * u1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sv[k * TILE] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
+    for (int k = 0; k < 3; ++k) sv[k * PSFM_SVS] = g.R[k] * d0 + g.R[3 + k] * d1 + g.R[6 + k] * d2;
   }
   __syncthreads();
   const int cnp = sm.cap_np;

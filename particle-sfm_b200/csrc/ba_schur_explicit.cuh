@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_w(const T
   tile_fill_smem<TILE>(tc, sm, ti, a.pose16, nullptr, a.X, a.ht, a.wk, true);
   double* sv = sm.sv + tid;
 #pragma unroll
-  for (int k = 0; k < NVX; ++k) sv[k * TILE] = 0.0;
+  for (int k = 0; k < NVX; ++k) sv[k * PSFM_SVS] = 0.0;
   if (act) {
     ObsGeom g;
     load_geom<TILE>(sm, ls, lp, g);
@@ -110,15 +110,15 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_w(const T
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * TILE] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
+        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * PSFM_SVS] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
     }
     if (a.intr >= 1) {
       const double zf = (g.w[2] + g.tz) * inv_f;
       const double jf0 = -a02 * zf, jf1 = -a12 * zf;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        sv[(9 + r) * TILE] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
-        sv[(15 + r) * TILE] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
+        sv[(9 + r) * PSFM_SVS] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
+        sv[(15 + r) * PSFM_SVS] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
       }
     }
   }
@@ -255,7 +255,7 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
   const double inv_f = (a.intr >= 1) ? 1.0 / __ldg(a.K) : 0.0;
   double* sv = sm.sv + tid;
 #pragma unroll
-  for (int k = 0; k < NVX2; ++k) sv[k * TILE] = 0.0;
+  for (int k = 0; k < NVX2; ++k) sv[k * PSFM_SVS] = 0.0;
   double W[6][3], WH[6][3];
 #pragma unroll
   for (int r = 0; r < 6; ++r)
@@ -297,19 +297,19 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * TILE] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
+        for (int c = 0; c < 3; ++c) sv[(3 * r + c) * PSFM_SVS] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
     }
     if (a.intr >= 1) {
       const double zf = (g.w[2] + g.tz) * inv_f;
       const double jf0 = -a02 * zf, jf1 = -a12 * zf;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        sv[(9 + r) * TILE] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
-        sv[(15 + r) * TILE] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
+        sv[(9 + r) * PSFM_SVS] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
+        sv[(15 + r) * PSFM_SVS] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
       }
     }
 #pragma unroll
-    for (int r = (ROT ? 0 : 3); r < 6; ++r) sv[(21 + r) * TILE] = -(W[r][0] * wh[0] + W[r][1] * wh[1] + W[r][2] * wh[2]);
+    for (int r = (ROT ? 0 : 3); r < 6; ++r) sv[(21 + r) * PSFM_SVS] = -(W[r][0] * wh[0] + W[r][1] * wh[1] + W[r][2] * wh[2]);
   }
   __syncthreads();
   {
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile_p(co
 
 template <int TILE>
 inline size_t pipe_smem_schur_tile(int cns, int cnp) {
-  return 2 * PipeStage<TILE>::bytes(false, true, 15, cns, cnp) + sizeof(double) * WW * TILE;
+  return 2 * PipeStage<TILE>::bytes(false, true, 15, cns, cnp) + sizeof(double) * WW * (TILE + 1);
 }
 
 // ---- tile-local pair structure (built once per problem)

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize_p(con
   sm.cap_ns = cns; sm.cap_np = cnp;
   sm.sv = reinterpret_cast<double*>(smem_raw + 2 * sb);
   sm.sw = nullptr;
-  sm.sred = sm.sv + 18 * TILE;
+  sm.sred = sm.sv + 18 * PSFM_SVS;
   sm.sx = nullptr;
   pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, 3, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
     view_stage<TILE>(sm, s, ti.base);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize_p(con
 
 template <int TILE>
 inline size_t pipe_smem_linearize(int cns, int cnp) {
-  return 2 * PipeStage<TILE>::bytes(true, false, 3, cns, cnp) + sizeof(double) * (18 * TILE + 9 * 32);
+  return 2 * PipeStage<TILE>::bytes(true, false, 3, cns, cnp) + sizeof(double) * (18 * (TILE + 1) + 9 * 32);
 }
 
 }  // namespace ba
