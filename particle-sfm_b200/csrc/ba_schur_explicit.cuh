@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) k_schur_pairs(const PairArgs a) {
 // tile kernels.
 
 constexpr int NVX2 = 27;   // NVX (21) | -(W w^) rot (3) | t (3)
-constexpr int WW = 37;     // shared-memory stride of one observation's [W (18) | W H~ (18)] (+1 pad)
+constexpr int PS = 19;     // shared-memory stride of one observation's record (18 doubles + 1 pad)
 
 struct StArgs {
   Lin L;
@@ -256,11 +256,11 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
   double* sv = sm.sv + tid;
 #pragma unroll
   for (int k = 0; k < NVX2; ++k) sv[k * PSFM_SVS] = 0.0;
-  double W[6][3], WH[6][3];
+  // compact per-observation factors kept for the pair phase (W = Jc' Jp and W H~ = Jc' Q are
+  // never formed in memory):  rec = [a00 a02 a12 | w (3) | Q = Jp H~ (2x3) | Jp (2x3)]
+  double rec[18];
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { W[r][k] = 0.0; WH[r][k] = 0.0; }
+  for (int k = 0; k < 18; ++k) rec[k] = 0.0;
   if (act) {
     ObsGeom g;
     load_geom<TILE>(sm, ls, lp, g);
@@ -270,11 +270,17 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { wkp[k] = sm.spt[(9 + k) * cnp + lp]; wh[k] = sm.spt[(12 + k) * cnp + lp]; }
-    double jp[2][3], jc[2][6];
+    double jp[2][3], jc[2][6], Q[2][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       jp[0][k] = a00 * g.R[k] + a02 * g.R[6 + k];
       jp[1][k] = a00 * g.R[3 + k] + a12 * g.R[6 + k];
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      Q[m][0] = jp[m][0] * hv[0] + jp[m][1] * hv[1] + jp[m][2] * hv[2];
+      Q[m][1] = jp[m][0] * hv[1] + jp[m][1] * hv[3] + jp[m][2] * hv[4];
+      Q[m][2] = jp[m][0] * hv[2] + jp[m][1] * hv[4] + jp[m][2] * hv[5];
     }
     if (ROT) {
       jc[0][0] = 2.0 * a02 * g.w[1]; jc[0][1] = 2.0 * (a00 * g.w[2] - a02 * g.w[0]); jc[0][2] = -2.0 * a00 * g.w[1];
@@ -285,31 +291,32 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     }
     jc[0][3] = a00; jc[0][4] = 0.0; jc[0][5] = a02;
     jc[1][3] = 0.0; jc[1][4] = a00; jc[1][5] = a12;
+    rec[0] = a00; rec[1] = a02; rec[2] = a12;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) W[r][k] = jc[0][r] * jp[0][k] + jc[1][r] * jp[1][k];
-      WH[r][0] = W[r][0] * hv[0] + W[r][1] * hv[1] + W[r][2] * hv[2];
-      WH[r][1] = W[r][0] * hv[1] + W[r][1] * hv[3] + W[r][2] * hv[4];
-      WH[r][2] = W[r][0] * hv[2] + W[r][1] * hv[4] + W[r][2] * hv[5];
-    }
+    for (int k = 0; k < 3; ++k) { rec[3 + k] = g.w[k]; rec[6 + k] = Q[0][k]; rec[9 + k] = Q[1][k]; rec[12 + k] = jp[0][k]; rec[15 + k] = jp[1][k]; }
     if (ROT) {   // rot-t cross block of F'F: (Jr' Jt)[r][c]
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) sv[(3 * r + c) * PSFM_SVS] = jc[0][r] * jc[0][3 + c] + jc[1][r] * jc[1][3 + c];
     }
+    // per-image sums that need W = Jc' Jp and W H~ = Jc' Q contracted with a per-point 3-vector v:
+    // (W v)[r] = jc0[r] (jp0.v) + jc1[r] (jp1.v),   (W H~ v)[r] = jc0[r] (Q0.v) + jc1[r] (Q1.v)
     if (a.intr >= 1) {
       const double zf = (g.w[2] + g.tz) * inv_f;
       const double jf0 = -a02 * zf, jf1 = -a12 * zf;
+      const double qk0 = Q[0][0] * wkp[0] + Q[0][1] * wkp[1] + Q[0][2] * wkp[2];
+      const double qk1 = Q[1][0] * wkp[0] + Q[1][1] * wkp[1] + Q[1][2] * wkp[2];
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        sv[(9 + r) * PSFM_SVS] = jc[0][r] * jf0 + jc[1][r] * jf1;                               // F'G
-        sv[(15 + r) * PSFM_SVS] = -(WH[r][0] * wkp[0] + WH[r][1] * wkp[1] + WH[r][2] * wkp[2]);  // -(W H~) Wk'
+        sv[(9 + r) * PSFM_SVS] = jc[0][r] * jf0 + jc[1][r] * jf1;            // F'G
+        sv[(15 + r) * PSFM_SVS] = -(jc[0][r] * qk0 + jc[1][r] * qk1);          // -(W H~) Wk'
       }
     }
+    const double pw0 = jp[0][0] * wh[0] + jp[0][1] * wh[1] + jp[0][2] * wh[2];
+    const double pw1 = jp[1][0] * wh[0] + jp[1][1] * wh[1] + jp[1][2] * wh[2];
 #pragma unroll
-    for (int r = (ROT ? 0 : 3); r < 6; ++r) sv[(21 + r) * PSFM_SVS] = -(W[r][0] * wh[0] + W[r][1] * wh[1] + W[r][2] * wh[2]);
+    for (int r = (ROT ? 0 : 3); r < 6; ++r) sv[(21 + r) * PSFM_SVS] = -(jc[0][r] * pw0 + jc[1][r] * pw1);   // -(W w^)
   }
   __syncthreads();
   {
@@ -319,55 +326,91 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     });
   }
   __syncthreads();
-  // the reduction rows are dead: the same shared memory now holds [W | W H~] per observation
-  double* sww = sm.sv;
+  // the reduction rows are dead: the same shared memory now holds the per-observation records
+  double* srec = sm.sv;
   if (act) {
-    double* o = sww + (size_t)tid * WW;
+    double* o = srec + (size_t)tid * PS;
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { o[3 * r + k] = W[r][k]; o[18 + 3 * r + k] = WH[r][k]; }
+    for (int k = 0; k < 18; ++k) o[k] = rec[k];
   }
   __syncthreads();
   double* band = a.Sband + (size_t)(rep & a.nrep_mask) * a.band_stride;
-  // four lanes per task when rotations are free: (block rows 0-2 | 3-5) x (even | odd entries);
-  // the two entry parities are combined with one shuffle per element, each lane then issues
-  // nine of the eighteen REDs.  The trip count is uniform over the CTA (shuffles).
-  const int nq = (ROT ? 4 : 2) * nt;
+  // Pair tasks.  Block(i, j) = (W_i H~) W_j' = Jc_i' M Jc_j with the 2x2 M = Q_i Jp_j': per
+  // entry 24 shared-memory loads (the kernel is bound by shared-memory wavefronts, not by the
+  // fp64 pipe) and ~110 flops.  Two lanes per task (even | odd entries), the full 6x6 block in
+  // registers, one shuffle per element to combine, 18 REDs per lane.  Uniform trip count.
+  const int nq = 2 * nt;
   for (int q0 = 0; q0 < nq; q0 += TILE) {
     const int q = q0 + tid;
     const bool valid = q < nq;
-    const int t = t0 + (ROT ? (q >> 2) : (q >> 1));
-    const int half = ROT ? ((q >> 1) & 1) : 1, par = q & 1;
+    const int t = t0 + (q >> 1), par = q & 1;
     int e0 = 0, e1 = 0;
     if (valid) { const int2 rg = __ldg(a.task_rng + t); e0 = rg.x; e1 = rg.y; }
-    double acc[18];
+    double acc[36];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
     int e = e0 + par;
     unsigned int u_next = (e < e1) ? __ldg(a.entries + e) : 0u;
     for (; e < e1; e += 2) {
       const unsigned int u = u_next;
       if (e + 2 < e1) u_next = __ldg(a.entries + e + 2);
-      const double* A = sww + (size_t)(u >> 16) * WW + 18 + 9 * half;
-      const double* B = sww + (size_t)(u & 0xffffu) * WW;
-      double av[9], bv[18];
+      const double* Ci = srec + (size_t)(u >> 16) * PS;
+      const double* Cj = srec + (size_t)(u & 0xffffu) * PS;
+      // M = Q_i Jp_j'
+      double m00 = 0.0, m01 = 0.0, m10 = 0.0, m11 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) av[k] = A[k];
+      for (int k = 0; k < 3; ++k) {
+        const double qa = Ci[6 + k], qb = Ci[9 + k], pa = Cj[12 + k], pb = Cj[15 + k];
+        m00 = fma(qa, pa, m00); m01 = fma(qa, pb, m01); m10 = fma(qb, pa, m10); m11 = fma(qb, pb, m11);
+      }
+      // T = M Jc_j  (2 x 6)
+      double T0[6], T1[6];
+      {
+        const double b00 = Cj[0], b02 = Cj[1], b12 = Cj[2];
+        double j0[6], j1[6];
+        if (ROT) {
+          const double w0 = Cj[3], w1 = Cj[4], w2 = Cj[5];
+          j0[0] = 2.0 * b02 * w1; j0[1] = 2.0 * (b00 * w2 - b02 * w0); j0[2] = -2.0 * b00 * w1;
+          j1[0] = 2.0 * (b12 * w1 - b00 * w2); j1[1] = -2.0 * b12 * w0; j1[2] = 2.0 * b00 * w0;
+        } else {
 #pragma unroll
-      for (int k = 0; k < 18; ++k) bv[k] = B[k];
+          for (int k = 0; k < 3; ++k) { j0[k] = 0.0; j1[k] = 0.0; }
+        }
+        j0[3] = b00; j0[4] = 0.0; j0[5] = b02;
+        j1[3] = 0.0; j1[4] = b00; j1[5] = b12;
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 6; ++c) { T0[c] = m00 * j0[c] + m01 * j1[c]; T1[c] = m10 * j0[c] + m11 * j1[c]; }
+      }
+      // acc += Jc_i' T
+      {
+        const double c00 = Ci[0], c02 = Ci[1], c12 = Ci[2];
+        double i0[6], i1[6];
+        if (ROT) {
+          const double w0 = Ci[3], w1 = Ci[4], w2 = Ci[5];
+          i0[0] = 2.0 * c02 * w1; i0[1] = 2.0 * (c00 * w2 - c02 * w0); i0[2] = -2.0 * c00 * w1;
+          i1[0] = 2.0 * (c12 * w1 - c00 * w2); i1[1] = -2.0 * c12 * w0; i1[2] = 2.0 * c00 * w0;
+        } else {
 #pragma unroll
-        for (int c = 0; c < 6; ++c)   // three chained FMAs per element (no separate product sum)
-          acc[6 * r + c] = fma(av[3 * r + 2], bv[3 * c + 2], fma(av[3 * r + 1], bv[3 * c + 1], fma(av[3 * r], bv[3 * c], acc[6 * r + c])));
+          for (int k = 0; k < 3; ++k) { i0[k] = 0.0; i1[k] = 0.0; }
+        }
+        i0[3] = c00; i0[4] = 0.0; i0[5] = c02;
+        i1[3] = 0.0; i1[4] = c00; i1[5] = c12;
+#pragma unroll
+        for (int r = (ROT ? 0 : 3); r < 6; ++r)
+#pragma unroll
+          for (int c = (ROT ? 0 : 3); c < 6; ++c) acc[6 * r + c] = fma(i1[r], T1[c], fma(i0[r], T0[c], acc[6 * r + c]));
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 18; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    for (int k = 0; k < 36; ++k)
+      if (ROT || (k / 6 >= 3 && k % 6 >= 3)) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
     if (valid) {
-      double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * half + 9 * par;
+      double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * par;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) atomicAdd(dst + k, par ? acc[9 + k] : acc[k]);
+      for (int k = 0; k < 18; ++k) {
+        const double v = par ? acc[18 + k] : acc[k];
+        if (ROT || v != 0.0) atomicAdd(dst + k, v);      // rotation blocks are structurally zero without ROT
+      }
     }
   }
 }
@@ -376,7 +419,7 @@ template <int TILE, bool ROT>
 __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(const TileCtx tc, const StArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE> sm;
-  sm.carve(smem_raw, WW, 15, tc.cap_ns, tc.cap_np);
+  sm.carve(smem_raw, NVX2, 15, tc.cap_ns, tc.cap_np);
   const TileInfo ti = tile_header(tc);
   const int tid = threadIdx.x;
   const bool act = tid < ti.n;
@@ -422,7 +465,7 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile_p(co
 
 template <int TILE>
 inline size_t pipe_smem_schur_tile(int cns, int cnp) {
-  return 2 * PipeStage<TILE>::bytes(false, true, 15, cns, cnp) + sizeof(double) * WW * (TILE + 1);
+  return 2 * PipeStage<TILE>::bytes(false, true, 15, cns, cnp) + sizeof(double) * NVX2 * (TILE + 1);
 }
 
 // ---- tile-local pair structure (built once per problem)

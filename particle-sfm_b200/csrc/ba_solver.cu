@@ -848,7 +848,7 @@ void ensure_pairs(psfm_ba_solver* S) {
   }
   S->span = (S->bw - 5) / 6;
   {
-    const size_t smem256 = TileSmem<256>::bytes(WW, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(WW, 15, S->cap_ns, S->cap_np);
+    const size_t smem256 = TileSmem<256>::bytes(NVX2, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(NVX2, 15, S->cap_ns, S->cap_np);
     const size_t smem = S->tile == 256 ? smem256 : smem512;
     S->fused = smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
   }
@@ -1029,7 +1029,7 @@ bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
     ps.obs_a = S->d_a.p; ps.p6 = S->d_hinv.p; ps.p3a = S->d_wk.p; ps.p3b = S->d_w.p;
     PSFM_PIPE_LAUNCH(k_schur_tile_p, pipe_smem_schur_tile, S, c.rot, ps, w);
   } else {
-    PSFM_TILE_LAUNCH(k_schur_tile, WW, 15, S, c.rot, w);
+    PSFM_TILE_LAUNCH(k_schur_tile, NVX2, 15, S, c.rot, w);
   }
   mark(S->ev_sw, false);
   mark(S->ev_chol, true);

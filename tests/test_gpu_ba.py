@@ -215,12 +215,12 @@ def _mixed_track_problem(frames, long_len, seed):
                           a.pose_constant, a.tvec_constant_mask, a.camera_constant)
 
 
-@pytest.mark.parametrize("frames,long_len,fused", [(320, 300, 1), (520, 500, 0)])
+@pytest.mark.parametrize("frames,long_len,fused", [(320, 300, 1), (520, 500, 1)])
 def test_exact_mode_wide_tiles(gpu, frames, long_len, fused):
-    """Tracks of 300 observations run the fused Schur kernel on 512-wide tiles; with tracks of
-    500 observations over 520 images the W buffer plus the per-image staging exceed the shared
-    memory of an SM and the unfused k_schur_w + k_schur_pairs path takes over.  Both must
-    reproduce the oracle's exact step."""
+    """Tracks of 300 / 500 observations run the fused Schur kernel on 512-wide tiles (per-image
+    staging for up to 520 images next to the per-observation records in shared memory); the
+    unfused k_schur_w + k_schur_pairs path is covered by test_code_paths_agree.  Both sizes
+    must reproduce the oracle's exact step."""
     p = _mixed_track_problem(frames, long_len, seed=30)
     o = _opts(True, True, _abi.SOLVER_EXACT_SCHUR)
     o.max_num_iterations = 3
