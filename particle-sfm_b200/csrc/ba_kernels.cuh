@@ -786,7 +786,7 @@ struct BackArgs {
 };
 
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 4 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<TILE> sm;
   sm.carve(smem_raw, 3, 12, tc.cap_ns, tc.cap_np);

@@ -44,15 +44,21 @@ __global__ void k_fill(double* p, double v, size_t n) {
 }
 
 // dst[i] (+)= sum over replicas of src[r][i]; the replicas are zeroed for the next use
-__global__ void k_fold_replicas(double* dst, double* rep, size_t n, size_t stride, int nrep, const double* scale,
-                                const int* skip_flag) {
+__global__ void k_fold_replicas(double* __restrict__ dst, double* __restrict__ rep, size_t n, size_t stride, int nrep,
+                                const double* __restrict__ scale, const int* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag != 0) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
-  for (int r = 0; r < nrep; ++r) {
-    s += rep[(size_t)r * stride + i];
-    rep[(size_t)r * stride + i] = 0.0;
+  for (int r0 = 0; r0 < nrep; r0 += 8) {        // eight independent loads in flight, fixed summation order
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (r0 + u < nrep) ? rep[(size_t)(r0 + u) * stride + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < nrep) rep[(size_t)(r0 + u) * stride + i] = 0.0;
   }
   dst[i] = scale ? scale[i] * s : s;
 }
