@@ -4,13 +4,16 @@
 // SPARSE_SCHUR, bundle_adjustment.cc:276-286): Ceres' SchurEliminator forms
 //     S = F'F + D_c^2 - sum_p (F'E)_p (E'E + D_p^2)^-1 (E'F)_p
 // and factorises it.  This file does the same on the GPU:
-//   k_schur_w        per observation W_i = Jc_i' Jp_i (6x3) and W_i H~_p, stored AoS;
-//                    per image the rot-t cross block of F'F and the focal column terms
-//   pair structure   all (i, j) observation pairs of a point grouped by image pair (a <= b)
+//   k_schur_tile[_p] FUSED path: per observation the compact factors [D | w | Q = Jp H~ | Jp]
+//                    stay in shared memory; per-image cross blocks / focal column / rhs
+//                    correction; the tile's pair tasks sum (W_i H~) W_j' = Jc_i' (Q_i Jp_j') Jc_j
+//                    into the band-block accumulator Sband[a][b - a][36]
+//   pair structure   all (i, j) observation pairs of a point keyed by (tile, image a, image b)
 //                    (built once per problem with radix sort / run-length encode)
-//   k_schur_pairs    one CTA per chunk of one image-pair block: sum_i,j (W_i H~) W_j'
+//   k_schur_w, k_schur_pairs   unfused fallback through HBM (W, W H~ per observation, AoS),
+//                    used when a tile's staging does not fit in shared memory
 //   k_schur_assemble dense symmetric S (6F+3C)^2 with Jacobi scaling, LM diagonal, gauge
-//   k_chol_banded    in-place banded(+arrow) Cholesky and the two triangular solves,
+//   k_chol_blocked   cooperative blocked banded(+arrow) Cholesky and the triangular solves,
 //                    band = 6 * (longest image span of a track) — video tracks make S banded
 // Everything accumulates with the UNSCALED factored Jacobian (see ba_kernels.cuh); the
 // scaling diag(s) is applied in k_schur_assemble.
@@ -640,77 +643,6 @@ __global__ void k_schur_assemble_finish(const AsmArgs a) {
   else a.S[(size_t)s * a.lda + s] = 1.0;
   a.S[(size_t)a.NS * a.lda + s] = a.rhs[s];      // rhs as an extra (arrow) row: its factor row is L^-1 b
 }
-
-// ------------------------------------------------------------------ banded (+ arrow) Cholesky, single CTA
-
-// S is symmetric positive definite with S[i][j] == 0 for |i - j| > bw among the first nb
-// rows; the last (n - nb) rows/columns (shared intrinsics) are dense ("arrow").  In-place
-// lower factor, then L y = b, L' x = y.  fail[0] = 1 when a pivot is not positive.
-__global__ void __launch_bounds__(1024) k_chol_banded(double* S, int n, int nb, int bw, const double* b, double* x, int* fail) {
-  __shared__ double s_d;
-  __shared__ int s_bad;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) s_bad = 0;
-  __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      const double d = S[(size_t)j * n + j];
-      if (!(d > 0.0) || isinf(d)) s_bad = 1;
-      s_d = sqrt(d);
-      S[(size_t)j * n + j] = s_d;
-    }
-    __syncthreads();
-    if (s_bad) break;
-    const double dj = s_d;
-    // rows below j that can be non-zero: band rows, then the arrow rows
-    const int r1 = (j < nb) ? min(nb, j + bw + 1) : n;      // band part end (exclusive)
-    const int nband = max(0, r1 - (j + 1));
-    const int arrow0 = max(nb, j + 1);
-    const int nrows = nband + (n - arrow0) * (j < nb ? 1 : 0);
-    const int total = (j < nb) ? nrows : (n - (j + 1));
-    for (int t = tid; t < total; t += nt) {
-      const int i = (j < nb) ? (t < nband ? j + 1 + t : arrow0 + (t - nband)) : j + 1 + t;
-      S[(size_t)i * n + j] /= dj;
-    }
-    __syncthreads();
-    // trailing update (lower triangle of the active window)
-    const long long pairs = (long long)total * (total + 1) / 2;
-    for (long long q = tid; q < pairs; q += nt) {
-      // q -> (u >= v) in the triangular index space
-      int u = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
-      while ((long long)(u + 1) * (u + 2) / 2 <= q) ++u;
-      while ((long long)u * (u + 1) / 2 > q) --u;
-      const int v = (int)(q - (long long)u * (u + 1) / 2);
-      const int iu = (j < nb) ? (u < nband ? j + 1 + u : arrow0 + (u - nband)) : j + 1 + u;
-      const int iv = (j < nb) ? (v < nband ? j + 1 + v : arrow0 + (v - nband)) : j + 1 + v;
-      S[(size_t)iu * n + iv] -= S[(size_t)iu * n + j] * S[(size_t)iv * n + j];
-    }
-    __syncthreads();
-  }
-  if (tid == 0) *fail = s_bad;
-  if (s_bad) return;
-  // forward: L y = b
-  __shared__ double sred[32];
-  for (int i = 0; i < n; ++i) {
-    const int k0 = (i < nb) ? max(0, i - bw) : 0;
-    double s = 0.0;
-    for (int k = k0 + tid; k < i; k += nt) s += S[(size_t)i * n + k] * x[k];
-    s = block_sum(s, sred);
-    if (tid == 0) x[i] = ((i < n ? b[i] : 0.0) - s) / S[(size_t)i * n + i];
-    __syncthreads();
-  }
-  // backward: L' x = y
-  for (int i = n - 1; i >= 0; --i) {
-    const int k1 = (i < nb) ? min(nb, i + bw + 1) : n;
-    double s = 0.0;
-    for (int k = i + 1 + tid; k < k1; k += nt) s += S[(size_t)k * n + i] * x[k];
-    if (i < nb) for (int k = max(nb, i + 1) + tid; k < n; k += nt) s += S[(size_t)k * n + i] * x[k];
-    s = block_sum(s, sred);
-    if (tid == 0) x[i] = (x[i] - s) / S[(size_t)i * n + i];
-    __syncthreads();
-  }
-}
-
 
 // ------------------------------------------------------------------ blocked, band-aware Cholesky (cooperative, multi-CTA)
 
