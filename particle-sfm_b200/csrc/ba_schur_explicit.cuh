@@ -661,8 +661,26 @@ struct CholArgs {
   int ns, lda, nb, bw;
   double* x;      // [ns]
   int* fail;
+  unsigned int* bar;          // grid barrier counter, zeroed before the launch
   unsigned long long* prof;   // optional [8]: SM cycles of CTA 0 per phase (PSFM_CHOL_PROFILE)
 };
+
+// Grid-wide barrier for the few (co-resident, cooperative launch) CTAs of k_chol_blocked: one
+// atomic per CTA on a monotone counter and an acquire spin — about half the cost of
+// cooperative_groups' grid.sync(), which this kernel pays twice per 32-column panel.
+__device__ __forceinline__ void chol_grid_barrier(unsigned int* counter, unsigned int& target) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ int chol_row_of(int pos, int c1, int nband, int arrow0) {
   return pos < nband ? c1 + pos : arrow0 + (pos - nband);
@@ -718,8 +736,7 @@ __device__ __noinline__ void chol_row_solve(double* __restrict__ row, int w, con
 }
 
 __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
-  namespace cgx = cooperative_groups;
-  cgx::grid_group grid = cgx::this_grid();
+  unsigned int bar_target = 0;
   __shared__ double sD[CB][CB + 1];
   __shared__ double sLi[CB][CB + 1];
   __shared__ double sLj[CB][CB + 1];
@@ -756,22 +773,17 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
       if (pos < npos) chol_row_solve(A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0, w, sD, sDinv);
     }
     PSFM_CHOL_TICK(1);
-    __threadfence();
-    grid.sync();
+    chol_grid_barrier(a.bar, bar_target);
     PSFM_CHOL_TICK(2);
-    // every CTA has finished reading the unfactored diagonal block: CTA 0 stores L11
-    if (blockIdx.x == 0)
-      for (int t = tid; t < w * w; t += 256) {
-        const int r = t / w, c = t % w;
-        if (c <= r) A[(size_t)(c0 + r) * lda + c0 + c] = sD[r][c];
-      }
+    // every CTA has finished reading the unfactored diagonal block: L11 is stored, rows shared out
+    for (int r = blockIdx.x; r < w; r += gridDim.x)
+      if (tid <= r) A[(size_t)(c0 + r) * lda + c0 + tid] = sD[r][tid];
     // ---- (3) trailing update of the tiles below/right of the panel
     const int ntile = (npos + CB - 1) / CB;
     const int npair = ntile * (ntile + 1) / 2;
     for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) {
-      int ti = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
-      while (ti * (ti + 1) / 2 > pr) --ti;
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;          // pr -> (ti, tj), tj <= ti; a handful of tiles
       const int tj = pr - ti * (ti + 1) / 2;
       __syncthreads();
       double* dst[4];
@@ -801,16 +813,20 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
       for (int u = 0; u < 4; ++u) {
         if (dst[u]) {
           const int r = (tid + 256 * u) / CB, c = (tid + 256 * u) % CB;
-          double s = 0.0;
-#pragma unroll 8
-          for (int k = 0; k < CB; ++k) s += sLi[r][k] * sLj[c][k];
-          *dst[u] = old[u] - s;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four chains: a dependent fp64 op costs ~25-30 cycles
+#pragma unroll
+          for (int k = 0; k < CB; k += 4) {
+            s0 = fma(sLi[r][k], sLj[c][k], s0);
+            s1 = fma(sLi[r][k + 1], sLj[c][k + 1], s1);
+            s2 = fma(sLi[r][k + 2], sLj[c][k + 2], s2);
+            s3 = fma(sLi[r][k + 3], sLj[c][k + 3], s3);
+          }
+          *dst[u] = old[u] - ((s0 + s1) + (s2 + s3));
         }
       }
     }
     PSFM_CHOL_TICK(3);
-    __threadfence();
-    grid.sync();
+    chol_grid_barrier(a.bar, bar_target);
     PSFM_CHOL_TICK(4);
   }
   if (blockIdx.x != 0) return;

@@ -135,6 +135,7 @@ struct psfm_ba_solver {
   DBuf<unsigned long long> d_entries;
   DBuf<int> d_blk_key, d_chunk_blk, d_cholfail;
   DBuf<unsigned long long> d_cholprof;
+  DBuf<unsigned int> d_cholbar;
   DBuf<long long> d_chunk_beg;
   DBuf<double> d_W, d_WH, d_xcam, d_xcamrep, d_Sblk, d_S;
   // fused tile path (k_schur_tile): tile-local pair tasks and the band-block accumulator
@@ -984,6 +985,9 @@ bool launch_cholesky(psfm_ba_solver* S) {
     }
     CholArgs ca;
     ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
+    if (S->d_cholbar.n == 0) S->d_cholbar.alloc(1, st);
+    S->d_cholbar.zero(st);
+    ca.bar = S->d_cholbar.p;
     static const bool want_prof = getenv("PSFM_CHOL_PROFILE") != nullptr;
     if (want_prof && S->d_cholprof.n == 0) { S->d_cholprof.alloc(8, st); S->d_cholprof.zero(st); }
     ca.prof = want_prof ? S->d_cholprof.p : nullptr;
