@@ -649,11 +649,12 @@ __global__ void k_schur_assemble_finish(const AsmArgs a) {
 // In-place lower Cholesky of the leading ns x ns part of A (row-major, leading dimension
 // lda), where A[i][j] == 0 for |i - j| > bw among the first nb rows and rows nb..ns-1 are
 // dense ("arrow": shared intrinsics).  Row ns of A holds the right-hand side b: it is
-// carried through the factorisation as one more arrow row, so that afterwards
-// A[ns][k] = (L^-1 b)[k]; CTA 0 then solves L' x = L^-1 b.  One cooperative launch:
-// per 32-column panel  (1) every CTA factors the 32x32 diagonal block redundantly in shared
-// memory, (2) the rows below are solved against it, (3) grid.sync, the trailing tiles inside
-// the band are updated, grid.sync.  fail[0] = 1 when a pivot is not positive.
+// carried through the factorisation as one more arrow row, so that its solved entries are
+// L^-1 b; CTA 0 then solves L' x = L^-1 b.  One cooperative launch: per 32-column panel
+// (1) every CTA factors the 32x32 diagonal block redundantly, (2) per trailing tile pair a CTA
+// solves the two row tiles it needs against it and updates its tile, (3) ONE grid barrier.
+// The factor lives in its own storage (Ld, Lp); A keeps the unsolved panels so that no CTA
+// has to wait for another one's row solves.  fail[0] = 1 when a pivot is not positive.
 constexpr int CB = 32;
 
 struct CholArgs {
@@ -662,6 +663,9 @@ struct CholArgs {
   double* x;      // [ns]
   int* fail;
   unsigned int* bar;          // grid barrier counter, zeroed before the launch
+  double* Lp;                 // [npanel][rmax][CB]  solved rows below each panel (the factor's off-diagonal part)
+  double* Ld;                 // [npanel][CB][CB]    diagonal blocks of the factor
+  int rmax;                   // rows reserved per panel in Lp
   unsigned long long* prof;   // optional [8]: SM cycles of CTA 0 per phase (PSFM_CHOL_PROFILE)
 };
 
@@ -695,7 +699,7 @@ __device__ __noinline__ bool chol_diag_warp(const double* __restrict__ A, int ld
   double arow[CB];
 #pragma unroll
   for (int c = 0; c < CB; ++c)
-    arow[c] = (lane < w && c <= lane) ? A[(size_t)lane * lda + c] : ((c == lane && lane >= w) ? 1.0 : 0.0);
+    arow[c] = (lane < w && c <= lane) ? __ldcg(A + (size_t)lane * lda + c) : ((c == lane && lane >= w) ? 1.0 : 0.0);
   bool bad = false;
   double myinv = 1.0;
 #pragma unroll
@@ -718,13 +722,14 @@ __device__ __noinline__ bool chol_diag_warp(const double* __restrict__ A, int ld
   return __any_sync(0xffffffffu, bad);
 }
 
-// One row x (w entries at row[0..w)) of the panel below the diagonal block: x L' = a, in
-// registers, right-looking so that the updates of one step are independent.
-__device__ __noinline__ void chol_row_solve(double* __restrict__ row, int w, const double (*sD)[CB + 1],
-                                            const double* sDinv) {
+// One row of the panel below the diagonal block: x L11' = a (registers, right-looking so that the
+// updates of one step are independent), from the (unsolved) global row into a shared-memory tile
+// row and, when lprow != nullptr, into the factor storage.
+__device__ __noinline__ void chol_row_solve_to(const double* __restrict__ grow, int w, const double (*sD)[CB + 1],
+                                               const double* sDinv, double* __restrict__ srow, double* __restrict__ lprow) {
   double xr[CB];
 #pragma unroll
-  for (int k = 0; k < CB; ++k) xr[k] = (k < w) ? row[k] : 0.0;
+  for (int k = 0; k < CB; ++k) xr[k] = (k < w) ? __ldcg(grow + k) : 0.0;
 #pragma unroll
   for (int k = 0; k < CB; ++k) {
     xr[k] *= sDinv[k];
@@ -732,7 +737,11 @@ __device__ __noinline__ void chol_row_solve(double* __restrict__ row, int w, con
     for (int m = k + 1; m < CB; ++m) xr[m] -= xr[k] * sD[m][k];
   }
 #pragma unroll
-  for (int k = 0; k < CB; ++k) if (k < w) row[k] = xr[k];
+  for (int k = 0; k < CB; ++k) srow[k] = xr[k];
+  if (lprow) {
+#pragma unroll
+    for (int k = 0; k < CB; ++k) lprow[k] = xr[k];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
@@ -767,18 +776,15 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
     const int nband = max(0, rb - c1);
     const int arrow0 = max(a.nb, c1);
     const int npos = nband + (nrows - arrow0);
-    // ---- (2) solve X L11' = A21 for these rows (one thread per row, registers)
-    for (int q = blockIdx.x * 256; q < npos; q += gridDim.x * 256) {
-      const int pos = q + tid;
-      if (pos < npos) chol_row_solve(A + (size_t)chol_row_of(pos, c1, nband, arrow0) * lda + c0, w, sD, sDinv);
-    }
-    PSFM_CHOL_TICK(1);
-    chol_grid_barrier(a.bar, bar_target);
-    PSFM_CHOL_TICK(2);
-    // every CTA has finished reading the unfactored diagonal block: L11 is stored, rows shared out
-    for (int r = blockIdx.x; r < w; r += gridDim.x)
-      if (tid <= r) A[(size_t)(c0 + r) * lda + c0 + tid] = sD[r][tid];
-    // ---- (3) trailing update of the tiles below/right of the panel
+    const int p = c0 / CB;
+    // the factor's diagonal block goes to its own storage (the unfactored block in A is still
+    // being read by slower CTAs)
+    if (blockIdx.x == 0)
+      for (int t = tid; t < CB * CB; t += 256) a.Ld[(size_t)p * CB * CB + t] = sD[t / CB][t % CB];
+    // ---- (2+3) per tile pair of the rows below the panel: this CTA solves the two row tiles
+    //      it needs itself (X L11' = A21, from the UNSOLVED panel in A: nobody waits for a
+    //      row-solve phase of another CTA), then updates its trailing tile.  Solved rows are
+    //      stored to Lp by the CTA of pair (ti, 0).  ONE grid barrier per panel.
     const int ntile = (npos + CB - 1) / CB;
     const int npair = ntile * (ntile + 1) / 2;
     for (int pr = blockIdx.x; pr < npair; pr += gridDim.x) {
@@ -786,6 +792,21 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
       while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;          // pr -> (ti, tj), tj <= ti; a handful of tiles
       const int tj = pr - ti * (ti + 1) / 2;
       __syncthreads();
+      if (tid < 2 * CB) {
+        const int which = tid >> 5, lr = tid & 31;
+        const int pos = (which ? tj : ti) * CB + lr;
+        double* srow = which ? sLj[lr] : sLi[lr];
+        if (!(which && ti == tj)) {
+          if (pos < npos) {
+            const int g = chol_row_of(pos, c1, nband, arrow0);
+            double* lprow = (!which && tj == 0) ? a.Lp + ((size_t)p * a.rmax + pos) * CB : nullptr;
+            chol_row_solve_to(A + (size_t)g * lda + c0, w, sD, sDinv, srow, lprow);
+          } else {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) srow[k] = 0.0;
+          }
+        }
+      }
       double* dst[4];
       double old[4];
 #pragma unroll
@@ -798,17 +819,15 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
           const int gi = chol_row_of(pi, c1, nband, arrow0), gj = chol_row_of(pj, c1, nband, arrow0);
           if (gj < ns) {       // the rhs row has no column
             dst[u] = A + (size_t)gi * lda + gj;
-            old[u] = *dst[u];
+            old[u] = __ldcg(dst[u]);
           }
         }
       }
-      for (int t = tid; t < CB * CB; t += 256) {
-        const int r = t / CB, c = t % CB;
-        const int pi = ti * CB + r, pj = tj * CB + r;
-        sLi[r][c] = (pi < npos && c < w) ? A[(size_t)chol_row_of(pi, c1, nband, arrow0) * lda + c0 + c] : 0.0;
-        sLj[r][c] = (pj < npos && c < w) ? A[(size_t)chol_row_of(pj, c1, nband, arrow0) * lda + c0 + c] : 0.0;
-      }
       __syncthreads();
+      if (ti == tj) {
+        for (int t = tid; t < CB * CB; t += 256) sLj[t / CB][t % CB] = sLi[t / CB][t % CB];
+        __syncthreads();
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (dst[u]) {
@@ -832,23 +851,29 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
   if (blockIdx.x != 0) return;
   if (tid == 0) *a.fail = s_bad;
   if (s_bad) return;
-  // ---- back substitution L' x = y, y = A[ns][0..ns)   (CTA 0, panel by panel from the end)
+  // ---- back substitution L' x = y (CTA 0, panel by panel from the end); y = L^-1 b is the
+  //      solved rhs row, the last row below every panel in Lp
   __shared__ double sacc[8][CB];
-  for (int k = tid; k < ns; k += 256) a.x[k] = A[(size_t)ns * lda + k];
-  __syncthreads();
   const int npanel = (ns + CB - 1) / CB;
+  for (int t = tid; t < npanel * CB; t += 256) {
+    const int p = t / CB, c = t % CB, c0 = p * CB, w = min(CB, ns - c0), c1 = c0 + w;
+    if (c < w) {
+      const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
+      const int npos_all = max(0, rb - c1) + (nrows - max(a.nb, c1));
+      a.x[c0 + c] = __ldcg(a.Lp + ((size_t)p * a.rmax + (npos_all - 1)) * CB + c);
+    }
+  }
+  __syncthreads();
   for (int p = npanel - 1; p >= 0; --p) {
     const int c0 = p * CB, w = min(CB, ns - c0), c1 = c0 + w;
     const int rb = (c1 < a.nb) ? min(a.nb, c1 + a.bw) : c1;
     const int nband = max(0, rb - c1);
     const int arrow0 = max(a.nb, c1);
     const int npos = nband + (ns - arrow0);          // rhs row excluded
+    const double* Lp = a.Lp + (size_t)p * a.rmax * CB;
     // partial sums: column c of the panel, rows strided over the 8 row-groups
     const int c = tid % CB, g = tid / CB;
-    for (int t = tid; t < w * w; t += 256) {
-      const int r = t / w, cc = t % w;
-      if (cc <= r) sD[r][cc] = A[(size_t)(c0 + r) * lda + c0 + cc];
-    }
+    for (int t = tid; t < CB * CB; t += 256) sD[t / CB][t % CB] = __ldcg(a.Ld + (size_t)p * CB * CB + t);
     double s = 0.0;
     if (c < w) {
       int pos = g;
@@ -856,17 +881,13 @@ __global__ void __launch_bounds__(256) k_chol_blocked(const CholArgs a) {
         double av[4], xv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = chol_row_of(pos + 8 * u, c1, nband, arrow0);
-          av[u] = A[(size_t)r * lda + c0 + c];
-          xv[u] = a.x[r];
+          av[u] = __ldcg(Lp + (size_t)(pos + 8 * u) * CB + c);
+          xv[u] = a.x[chol_row_of(pos + 8 * u, c1, nband, arrow0)];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) s += av[u] * xv[u];
       }
-      for (; pos < npos; pos += 8) {
-        const int r = chol_row_of(pos, c1, nband, arrow0);
-        s += A[(size_t)r * lda + c0 + c] * a.x[r];
-      }
+      for (; pos < npos; pos += 8) s += __ldcg(Lp + (size_t)pos * CB + c) * a.x[chol_row_of(pos, c1, nband, arrow0)];
     }
     sacc[g][c] = s;
     __syncthreads();

@@ -136,6 +136,7 @@ struct psfm_ba_solver {
   DBuf<int> d_blk_key, d_chunk_blk, d_cholfail;
   DBuf<unsigned long long> d_cholprof;
   DBuf<unsigned int> d_cholbar;
+  DBuf<double> d_cholLp, d_cholLd;
   DBuf<long long> d_chunk_beg;
   DBuf<double> d_W, d_WH, d_xcam, d_xcamrep, d_Sblk, d_S;
   // fused tile path (k_schur_tile): tile-local pair tasks and the band-block accumulator
@@ -988,6 +989,13 @@ bool launch_cholesky(psfm_ba_solver* S) {
     if (S->d_cholbar.n == 0) S->d_cholbar.alloc(1, st);
     S->d_cholbar.zero(st);
     ca.bar = S->d_cholbar.p;
+    {
+      const int npanel = (S->NS + CB - 1) / CB;
+      const int rmax = std::min(bw + 1, nbnd) + (S->NS + 1 - nbnd) + 1;
+      if (S->d_cholLp.n < (size_t)npanel * rmax * CB) S->d_cholLp.alloc((size_t)npanel * rmax * CB, st);
+      if (S->d_cholLd.n < (size_t)npanel * CB * CB) S->d_cholLd.alloc((size_t)npanel * CB * CB, st);
+      ca.Lp = S->d_cholLp.p; ca.Ld = S->d_cholLd.p; ca.rmax = rmax;
+    }
     static const bool want_prof = getenv("PSFM_CHOL_PROFILE") != nullptr;
     if (want_prof && S->d_cholprof.n == 0) { S->d_cholprof.alloc(8, st); S->d_cholprof.zero(st); }
     ca.prof = want_prof ? S->d_cholprof.p : nullptr;
