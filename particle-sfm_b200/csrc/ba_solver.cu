@@ -268,6 +268,16 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   PSFM_CUDA(cudaStreamSynchronize(st));
   if (h_bad) { set_error("observation index out of range"); return PSFM_ERR_INVALID; }
   tm.mark("upload + count + order points");
+  // sort observations by (internal point, image) NOW: it only needs the point ranks, and runs on
+  // the device while the host packs the tiles below (radix sort is stable => ties keep input order)
+  S->d_obs_img.alloc(M, st); S->d_obs_pt.alloc(M, st); S->d_obs_xy.alloc(M, st); S->d_obs_orig.alloc(M, st);
+  if (M) {
+    k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
+    need = tmp_bytes + 256;
+    cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, idx.p, S->d_obs_orig.p, M, 0, 32 + pbits, st);
+    k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy.p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
+    PSFM_LAUNCH_CHECK();
+  }
   for (int i = 0; i < F; ++i) if (h_has[i]) { S->img_has_obs[i] = 1; S->cam_has_obs[S->image_camera[i]] = 1; }
   int P = 0, maxL = 0;
   while (P < Pt && h_cs[P] > 0) ++P;           // observed points come first
@@ -300,17 +310,8 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   S->d_tile_pt.alloc(T + 1, st); S->d_tile_pt.upload(tile_pt.data(), T + 1, st);
   S->d_pt_ptr.alloc(P + 1, st); S->d_pt_ptr.upload(pt_ptr.data(), P + 1, st);
   tm.mark("tiles (host greedy)");
-  // sort observations by (internal point, image); radix sort is stable => ties keep input order
-  S->d_obs_img.alloc(M, st); S->d_obs_pt.alloc(M, st); S->d_obs_xy.alloc(M, st); S->d_obs_orig.alloc(M, st);
   S->d_tile_perm.alloc((size_t)M + 2, st); S->d_obs_lseg.alloc((size_t)M + 2, st); S->d_obs_lpt.alloc((size_t)M + 2, st);
   S->d_cseg_ptr.alloc((size_t)T + 1, st);
-  if (M) {
-    k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
-    need = tmp_bytes + 256;
-    cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, idx.p, S->d_obs_orig.p, M, 0, 32 + pbits, st);
-    k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy.p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
-    PSFM_LAUNCH_CHECK();
-  }
   // per tile: image order, local indices, segments
   tile_ns.alloc((size_t)T + 1, st);
   PSFM_CUDA(cudaMemsetAsync(tile_ns.p, 0, sizeof(int) * ((size_t)T + 1), st));
