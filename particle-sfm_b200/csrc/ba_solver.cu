@@ -811,10 +811,12 @@ void ensure_pairs(psfm_ba_solver* S) {
   DBuf<int> ucount, nruns;
   cnt.alloc((size_t)M + 1, st); span.alloc(1, st); span.zero(st);
   PSFM_CUDA(cudaMemsetAsync(cnt.p + M, 0, sizeof(int), st));
-  k_pair_count<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, M, cnt.p);
-  PSFM_LAUNCH_CHECK();
-  k_point_span<<<grid_for(S->P), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_img.p, S->P, span.p);
-  PSFM_LAUNCH_CHECK();
+  if (M) {   // a rank of a sharded problem may own no observation at all
+    k_pair_count<<<grid_for(M), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_pt.p, S->d_obs_img.p, M, cnt.p);
+    PSFM_LAUNCH_CHECK();
+    k_point_span<<<grid_for(S->P), 256, 0, st>>>(S->d_pt_ptr.p, S->d_obs_img.p, S->P, span.p);
+    PSFM_LAUNCH_CHECK();
+  }
   // exclusive scan of the per-observation entry counts (64-bit total)
   DBuf<long long> ptr64;
   ptr64.alloc((size_t)M + 1, st);
@@ -840,6 +842,18 @@ void ensure_pairs(psfm_ba_solver* S) {
     S->bw = 6 * h_span + 5;
   }
   if (S->npairs >= (1ll << 31)) { set_error("too many observation pairs for the explicit Schur complement"); throw CudaFail{PSFM_ERR_UNSUPPORTED}; }
+  if (M == 0) {   // nothing to contribute: zero accumulators that still take part in the all-reduces
+    S->span = (S->bw - 5) / 6;
+    S->fused = true; S->ntasks = 0;
+    S->band_n = (size_t)F * (S->span + 1) * 36; S->band_nrep = 1;
+    S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
+    S->d_bandrep.alloc(S->band_n, st); S->d_bandrep.zero(st);
+    S->d_xcamrep.alloc((size_t)NREP * F * NVX2, st); S->d_xcamrep.zero(st);
+    S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), st); S->d_cholfail.alloc(1, st);
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->pairs_ready = true;
+    return;
+  }
   const size_t NPr = (size_t)S->npairs;
   // 32-bit offsets for the fill kernel
   DBuf<int> ptr32; ptr32.alloc((size_t)M + 1, st);
