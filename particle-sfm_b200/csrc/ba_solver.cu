@@ -106,6 +106,7 @@ struct psfm_ba_solver {
   std::vector<int> obs_orig;     // sorted observation -> caller's observation index
   std::vector<int> image_camera;
   std::vector<unsigned char> pose_constant, tvec_mask, camera_constant, img_has_obs, cam_has_obs;
+  int flags_world = 1;           // world size for which img_has_obs / cam_has_obs have been made global
   // host state (caller layout)
   std::vector<double> h_qvec, h_tvec, h_K;   // the points' state of record is pin_state's X part (tile order, own points only)
   // device structure
@@ -1202,6 +1203,28 @@ int count_observed_points_all_ranks(psfm_ba_solver* S) {
   return (int)(S->hs->x2 + 0.5);
 }
 
+// Sharded problems: whether an image / a camera has observations — i.e. whether Ceres would add
+// its parameter block at all (bundle_adjustment.cc:348-366) — is a property of the WHOLE problem.
+// A shard that happens not to see an image must still treat its pose as variable, otherwise the
+// ranks disagree on the active unknowns.  Max all-reduce of the per-rank flags, once per world.
+void sync_observed_flags(psfm_ba_solver* S) {
+  const int world = dist::world_size();
+  if (world <= 1 || S->flags_world == world) return;
+  const int n = S->F + S->C;
+  std::vector<double> h((size_t)n);
+  for (int i = 0; i < S->F; ++i) h[i] = S->img_has_obs[i] ? 1.0 : 0.0;
+  for (int c = 0; c < S->C; ++c) h[(size_t)S->F + c] = S->cam_has_obs[c] ? 1.0 : 0.0;
+  DBuf<double> d;
+  d.alloc((size_t)n, S->stream);
+  d.upload(h.data(), (size_t)n, S->stream);
+  dist::allreduce_max(d.p, (size_t)n, S->stream);
+  PSFM_CUDA(cudaMemcpyAsync(h.data(), d.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, S->stream));
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  for (int i = 0; i < S->F; ++i) S->img_has_obs[i] = h[i] > 0.5 ? 1 : 0;
+  for (int c = 0; c < S->C; ++c) S->cam_has_obs[c] = h[(size_t)S->F + c] > 0.5 ? 1 : 0;
+  S->flags_world = world;
+}
+
 int total_observations_all_ranks(psfm_ba_solver* S) {
   if (dist::world_size() == 1) return S->M;
   k_fill<<<1, 32, 0, S->stream>>>(S->d_x2.p, (double)S->M, 1);
@@ -1224,6 +1247,7 @@ void print_summary(const psfm_ba_summary& s) {
 
 int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* out) {
   RunCfg c;
+  sync_observed_flags(S);
   int rc = resolve_cfg(S, opts, c);
   if (rc != PSFM_OK) return rc;
   const psfm_ba_options& o = c.o;
@@ -1475,6 +1499,7 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
   if (!S) return PSFM_ERR_INVALID;
   try {
     RunCfg c;
+    sync_observed_flags(S);
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
       upload_state(S);
@@ -1517,6 +1542,7 @@ extern "C" int psfm_ba_linear_step(psfm_ba_solver* S, const psfm_ba_options* opt
   if (!S) return PSFM_ERR_INVALID;
   try {
     RunCfg c;
+    sync_observed_flags(S);
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
       S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
