@@ -12,8 +12,9 @@ rotations + focal length refined).
 
 `value`  = observations / second of solve = M / t_step, problem resident in HBM
            (observations, structure uploaded once; the state is re-set every step).
-`e2e`    = same metric through psfm_ba_solve() on HOST buffers: flattening, H2D of
-           observations/state, solve, D2H of the result inside the timed region.
+`e2e`    = same metric through psfm_ba_solve() on pinned HOST buffers: H2D of
+           observations/state, device-side flattening, pair structure, solve, D2H of the
+           result — all inside the timed region.
 The line also carries the HP1 number (trajectory optimiser, pts/s) under "traj_opt".
 
 `--impl reference` times the CPU oracle port (the reference's algorithm choices: exact
