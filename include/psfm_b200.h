@@ -275,6 +275,19 @@ int psfm_ba_evaluate(psfm_ba_solver* s, const psfm_ba_options* opts, double* cos
 int psfm_ba_linear_step(psfm_ba_solver* s, const psfm_ba_options* opts, double radius,
                         double* step_cam, double* step_pts, int32_t* num_linear_iterations);
 
+/* Measured fp64 roof of the current device (bench.py's roofline denominator for the kernels
+   that are bounded by the fp64 FMA pipe rather than by HBM): sustained fused multiply-adds
+   per second over the whole chip, and the latency in SM cycles of one dependent DFMA. */
+int psfm_measure_dfma(double* dfma_per_second, double* dependent_latency_cycles);
+
+/* Diagnostic used by the parity tests: solve one banded(+arrow) SPD system with the
+   single-CTA band Cholesky the exact-Schur mode uses (csrc/ba_band_chol.cuh).
+     A   [n][n] row-major symmetric, n = nb + 3: A[i][j] == 0 for |i - j| > bw among the
+         first nb rows/columns, the last 3 rows/columns are dense (the shared camera)
+     b   [n]     x [n] receives the solution.  Returns PSFM_OK, PSFM_ERR_INVALID when the
+   matrix is not positive definite, PSFM_ERR_UNSUPPORTED when bw exceeds the register window. */
+int psfm_ba_band_solve(const double* A, const double* b, int32_t nb, int32_t bw, double* x);
+
 /* ------------------------------------------------------------------------- */
 /* Multi-GPU (HP2): points sharded across ranks, one all-reduce of the         */
 /* camera-side vector per PCG step.                            */

@@ -20,8 +20,8 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libpsfm_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("ba_oracle.c", "traj_oracle.c", "psfm_oracle.h",
-                                             "ceres_semantics.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ba_oracle.c", "ba_schur_blocks.h", "traj_oracle.c", "psfm_oracle.h",
+                                             "ceres_semantics.h", "Makefile")]
     srcs.append(os.path.join(_ROOT, "include", "psfm_b200.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "MAKEFLAGS": ""})

@@ -44,6 +44,15 @@ static double wall_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* PSFM_ORACLE_TIMING=1: wall time per phase of a solve, printed to stderr (where does the CPU
+   baseline spend its time) */
+static double g_tm[8];
+static int g_tm_on = -1;
+#define TM_BEGIN() const double tm__0 = (g_tm_on > 0) ? wall_s() : 0.0
+#define TM_END(slot) do { if (g_tm_on > 0) g_tm[slot] += wall_s() - tm__0; } while (0)
+
+#include "ba_schur_blocks.h"
+
 int psfm_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -59,7 +68,14 @@ typedef struct {
   int nthreads;
   /* structure */
   int* pt_ptr;   /* P+1 */
-  int* pt_obs;   /* M: observation ids grouped by point */
+  int* pt_obs;   /* M: observation ids grouped by point (identity: see spb) */
+  /* Internal observation order = grouped by point, like Ceres after
+     ReorderProgramForSchurTypeLinearSolver (rows of an e-block are contiguous): `pb` points at
+     `spb`, a copy of the caller's problem whose observation arrays are the sorted ones, so every
+     pass over the stored Jacobian streams through memory. */
+  psfm_ba_problem spb;
+  int32_t* s_img; int32_t* s_pt; double* s_xy;
+  int* orig;     /* M: sorted position -> caller's observation index */
   unsigned char* slot_active; /* NS */
   unsigned char* img_has_obs; /* F */
   unsigned char* cam_has_obs; /* C */
@@ -89,6 +105,8 @@ typedef struct {
   double* tbuf;   /* per-thread scratch */
   size_t tbuf_stride;
   int num_linear_iterations;
+  sblocks_t sb;   /* block-sparse reduced system (single shared camera): ba_schur_blocks.h */
+  int sb_unusable;
 } ctx_t;
 
 /* ---------------------------------------------------------------- small math */
@@ -893,17 +911,43 @@ static int resolve_solver(const ctx_t* c) {
    returns 0 ok, 2 failure */
 static int linear_solve(ctx_t* c, int solver) {
   const int NS = c->NS, P = c->P;
-  jt_r(c, c->gs_c, c->gs_p); /* scaled-J gradient */
-  if (build_point_blocks(c)) return 2;
+  { TM_BEGIN(); jt_r(c, c->gs_c, c->gs_p); /* scaled-J gradient */
+    if (build_point_blocks(c)) return 2; TM_END(1); }
   double* yc = c->step_c;
   double* yp = c->step_p;
   c->num_linear_iterations = 0;
   if (solver == PSFM_BA_SOLVER_EXACT_SCHUR) {
-    if (!c->S) c->S = (double*)malloc(sizeof(double) * (size_t)NS * NS);
-    build_schur_dense(c, c->S);
-    schur_rhs(c, yc);
-    if (chol_lower(c->S, NS, c->nthreads)) return 2;
-    chol_solve(c->S, NS, yc);
+    /* SPARSE_SCHUR restatement (block-sparse S, band Cholesky) for the pipeline's single shared
+       camera; PSFM_ORACLE_DENSE_SCHUR=1 forces the general dense assembly (the two are compared
+       in tests/test_oracle_ba.py) */
+    if (c->C == 1 && !c->sb.ready && !c->sb_unusable) {
+      if (getenv("PSFM_ORACLE_DENSE_SCHUR") ||
+          sblocks_pattern(&c->sb, c->F, P, c->pt_ptr, c->pt_obs, c->pb->obs_image, c->nthreads)) {
+        sblocks_free(&c->sb);
+        c->sb_unusable = 1;
+      }
+    }
+    if (c->sb.ready) {
+      { TM_BEGIN(); sblocks_assemble(&c->sb, c->F, P, c->pt_ptr, c->pt_obs, c->pb->obs_image, c->Jc, c->Jp, c->Jk, c->Hinv, c->nthreads); TM_END(2); }
+      { TM_BEGIN(); schur_rhs(c, yc); TM_END(3); }
+      if (2 * (6 * c->sb.span + 5) < 6 * c->F) {
+        TM_BEGIN();
+        const int bad = sblocks_band_solve(&c->sb, c->F, c->slot_active, c->D_c, yc);
+        TM_END(4);
+        if (bad) return 2;
+      } else {
+        if (!c->S) c->S = (double*)malloc(sizeof(double) * (size_t)NS * NS);
+        sblocks_to_dense(&c->sb, c->F, c->slot_active, c->D_c, c->S);
+        if (chol_lower(c->S, NS, c->nthreads)) return 2;
+        chol_solve(c->S, NS, yc);
+      }
+    } else {
+      if (!c->S) c->S = (double*)malloc(sizeof(double) * (size_t)NS * NS);
+      build_schur_dense(c, c->S);
+      schur_rhs(c, yc);
+      if (chol_lower(c->S, NS, c->nthreads)) return 2;
+      chol_solve(c->S, NS, yc);
+    }
     c->num_linear_iterations = 1;
   } else {
     double* rhs = (double*)malloc(sizeof(double) * NS);
@@ -917,7 +961,7 @@ static int linear_solve(ctx_t* c, int solver) {
     free(rhs); free(Minv);
     if (term == 2) return 2;
   }
-  back_substitute(c, yc, yp);
+  { TM_BEGIN(); back_substitute(c, yc, yp); TM_END(5); }
   for (int k = 0; k < NS; ++k) { if (!isfinite(yc[k])) return 2; yc[k] = -yc[k]; }
   int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad) num_threads(c->nthreads)
@@ -1063,8 +1107,21 @@ static int ctx_init(ctx_t* c, const psfm_ba_problem* pb, const psfm_ba_options* 
   {
     int* fill = (int*)malloc(sizeof(int) * (size_t)(P + 1));
     memcpy(fill, c->pt_ptr, sizeof(int) * (size_t)(P + 1));
-    for (int i = 0; i < M; ++i) c->pt_obs[fill[pb->obs_point[i]]++] = i;
+    c->orig = (int*)malloc(sizeof(int) * (size_t)(M > 0 ? M : 1));
+    c->s_img = (int32_t*)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+    c->s_pt = (int32_t*)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+    c->s_xy = (double*)malloc(sizeof(double) * 2 * (size_t)(M > 0 ? M : 1));
+    for (int i = 0; i < M; ++i) c->orig[fill[pb->obs_point[i]]++] = i;     /* stable counting sort by point */
     free(fill);
+    for (int e = 0; e < M; ++e) {
+      const int i = c->orig[e];
+      c->pt_obs[e] = e;
+      c->s_img[e] = pb->obs_image[i]; c->s_pt[e] = pb->obs_point[i];
+      c->s_xy[2 * e] = pb->obs_xy[2 * i]; c->s_xy[2 * e + 1] = pb->obs_xy[2 * i + 1];
+    }
+    c->spb = *pb;
+    c->spb.obs_image = c->s_img; c->spb.obs_point = c->s_pt; c->spb.obs_xy = c->s_xy;
+    c->pb = &c->spb;
   }
   for (int i = 0; i < F; ++i) {
     const int constant_pose = !o->refine_extrinsics || (pb->pose_constant && pb->pose_constant[i]);
@@ -1121,6 +1178,8 @@ static void ctx_free(ctx_t* c) {
   free(c->scale_p); free(c->g_c); free(c->g_p); free(c->diag_c); free(c->diag_p); free(c->D_c);
   free(c->D_p); free(c->Hinv); free(c->gs_c); free(c->gs_p); free(c->step_c); free(c->step_p);
   free(c->S); free(c->Spriv); free(c->tbuf);
+  free(c->orig); free(c->s_img); free(c->s_pt); free(c->s_xy);
+  sblocks_free(&c->sb);
 }
 
 /* EvaluateGradientAndJacobian: cost, r, J, g = J'r (unscaled), optional scaling */
@@ -1181,7 +1240,10 @@ int psfm_oracle_ba_solve(psfm_ba_problem* pb, const psfm_ba_options* opts, psfm_
   int reuse_diagonal = 0;
   int num_consecutive_invalid = 0;
   int iteration = 0;
-  double x_cost = evaluate_gradient_and_jacobian(&c, 0);
+  if (g_tm_on < 0) g_tm_on = getenv("PSFM_ORACLE_TIMING") ? 1 : 0;
+  memset(g_tm, 0, sizeof(g_tm));
+  double x_cost;
+  { TM_BEGIN(); x_cost = evaluate_gradient_and_jacobian(&c, 0); TM_END(0); }
   double x_norm = sqrt(x_sqnorm(&c));
   double gmax = gradient_max_norm(&c);
   s.initial_cost = x_cost;
@@ -1218,8 +1280,8 @@ int psfm_oracle_ba_solve(psfm_ba_problem* pb, const psfm_ba_options* opts, psfm_
       continue;
     }
     num_consecutive_invalid = 0;
-    const double step_sq = make_candidate(&c);
-    const double cand_cost = evaluate(&c, c.qc, c.tc, c.Xc, c.Kc, 0);
+    double step_sq, cand_cost;
+    { TM_BEGIN(); step_sq = make_candidate(&c); cand_cost = evaluate(&c, c.qc, c.tc, c.Xc, c.Kc, 0); TM_END(6); }
     /* ParameterToleranceReached */
     const double step_norm = sqrt(step_sq);
     if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) { term = PSFM_TERM_CONVERGENCE_PARAMETER; break; }
@@ -1234,7 +1296,7 @@ int psfm_oracle_ba_solve(psfm_ba_problem* pb, const psfm_ba_options* opts, psfm_
       tmp = c.X; c.X = c.Xc; c.Xc = tmp;
       tmp = c.K; c.K = c.Kc; c.Kc = tmp;
       x_norm = sqrt(x_sqnorm(&c));
-      x_cost = evaluate_gradient_and_jacobian(&c, iteration);
+      { TM_BEGIN(); x_cost = evaluate_gradient_and_jacobian(&c, iteration); TM_END(0); }
       s.num_linearize++;
       gmax = gradient_max_norm(&c);
       /* StepAccepted */
@@ -1256,6 +1318,10 @@ int psfm_oracle_ba_solve(psfm_ba_problem* pb, const psfm_ba_options* opts, psfm_
   s.termination = term;
   s.final_cost = x_cost;
   s.total_time_in_seconds = wall_s() - t0;
+  if (g_tm_on > 0)
+    fprintf(stderr, "[oracle timing] %d threads, total %.3f s: linearise %.3f | J'r + point blocks %.3f | Schur assembly %.3f | rhs %.3f | "
+            "band Cholesky %.3f | back substitution %.3f | candidate + cost %.3f\n", c.nthreads, s.total_time_in_seconds,
+            g_tm[0], g_tm[1], g_tm[2], g_tm[3], g_tm[4], g_tm[5], g_tm[6]);
   /* write back (in place, like the reference) */
   memcpy(pb->qvec, c.q, sizeof(double) * 4 * (size_t)c.F);
   memcpy(pb->tvec, c.t, sizeof(double) * 3 * (size_t)c.F);
@@ -1286,7 +1352,11 @@ int psfm_oracle_ba_evaluate(const psfm_ba_problem* pb, const psfm_ba_options* op
   const double cst = evaluate(&c, c.q, c.t, c.X, c.K, 1);
   jt_r(&c, c.g_c, c.g_p);
   if (cost) *cost = cst;
-  if (residuals) memcpy(residuals, c.r, sizeof(double) * 2 * (size_t)c.M);
+  if (residuals)
+    for (int e = 0; e < c.M; ++e) {   /* back to the caller's observation order */
+      residuals[2 * (size_t)c.orig[e]] = c.r[2 * (size_t)e];
+      residuals[2 * (size_t)c.orig[e] + 1] = c.r[2 * (size_t)e + 1];
+    }
   if (gradient_cam) memcpy(gradient_cam, c.g_c, sizeof(double) * (size_t)c.NS);
   if (gradient_pts) memcpy(gradient_pts, c.g_p, sizeof(double) * 3 * (size_t)c.P);
   ctx_free(&c);
@@ -1301,9 +1371,12 @@ int psfm_oracle_ba_jacobians(const psfm_ba_problem* pb, const psfm_ba_options* o
   int rc = ctx_init(&c, pb, &o, 1);
   if (rc != PSFM_OK) { ctx_free(&c); return rc; }
   evaluate(&c, c.q, c.t, c.X, c.K, 1);
-  if (jc) memcpy(jc, c.Jc, sizeof(double) * 12 * (size_t)c.M);
-  if (jp) memcpy(jp, c.Jp, sizeof(double) * 6 * (size_t)c.M);
-  if (jk) memcpy(jk, c.Jk, sizeof(double) * 6 * (size_t)c.M);
+  for (int e = 0; e < c.M; ++e) {     /* back to the caller's observation order */
+    const size_t i = (size_t)c.orig[e];
+    if (jc) memcpy(jc + 12 * i, c.Jc + 12 * (size_t)e, sizeof(double) * 12);
+    if (jp) memcpy(jp + 6 * i, c.Jp + 6 * (size_t)e, sizeof(double) * 6);
+    if (jk) memcpy(jk + 6 * i, c.Jk + 6 * (size_t)e, sizeof(double) * 6);
+  }
   ctx_free(&c);
   return PSFM_OK;
 }

@@ -17,7 +17,7 @@ EXPORTS = [
     "psfm_traj_default_options", "psfm_traj_optimize", "psfm_traj_optimize_device",
     "psfm_ba_default_options", "psfm_ba_global_options", "psfm_ba_solve", "psfm_ba_create",
     "psfm_ba_set_state", "psfm_ba_run", "psfm_ba_get_state", "psfm_ba_destroy", "psfm_ba_evaluate",
-    "psfm_ba_linear_step", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
+    "psfm_ba_linear_step", "psfm_ba_band_solve", "psfm_measure_dfma", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
     "psfm_dist_rank", "psfm_dist_finalize",
 ]
 
@@ -58,6 +58,8 @@ def lib():
     L.psfm_ba_destroy.restype = None
     L.psfm_ba_evaluate.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), dp, dp, dp, dp]
     L.psfm_ba_linear_step.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), C.c_double, dp, dp, ip]
+    L.psfm_measure_dfma.argtypes = [dp, dp]
+    L.psfm_ba_band_solve.argtypes = [dp, dp, C.c_int32, C.c_int32, dp]
     L.psfm_dist_get_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.psfm_dist_init.argtypes = [C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
     L.psfm_dist_finalize.restype = None

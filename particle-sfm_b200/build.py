@@ -27,6 +27,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", CXX
 # bit-identical to the oracle compiled with -ffp-contract=off.
 UNITS = [
     ("common.cu", []),
+    ("microbench.cu", []),
     ("dist.cu", []),
     ("ba_solver.cu", []),
     ("traj_solver.cu", ["-fmad=false"]),

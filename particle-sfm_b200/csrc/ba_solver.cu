@@ -18,6 +18,7 @@
 #include "ba_small_kernels.cuh"
 #include "ba_structure.cuh"
 #include "ba_schur_explicit.cuh"
+#include "ba_band_chol.cuh"
 #include "dist.cuh"
 
 namespace psfm {
@@ -48,6 +49,8 @@ struct HostScalars {   // pinned
   double rep[2];       // |dcam|^2, |cam_c|^2
   double x2;
   PcgState pcg;
+  int chol_fail;
+  int pad;
 };
 
 }  // namespace ba
@@ -148,6 +151,10 @@ struct psfm_ba_solver {
   DBuf<int> d_task_slot, d_tile_task;
   DBuf<int2> d_task_rng;
   DBuf<double> d_xband, d_bandrep;      // d_xband = [xcam F*NVX2 | Sband band_n] (one all-reduce)
+  // single-CTA sliding-window band Cholesky (ba_band_chol.cuh): compact band matrix, factor, scratch
+  bool band_chol = false;
+  int bcW = 0, bcBw = 0, bcRows = 0;
+  DBuf<double> d_Ab, d_C4, d_Lr, d_La, d_dinv;
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   double* pin_state = nullptr;     // pinned staging of the state: pose (8F) | X (3P) | K (3C)
@@ -800,6 +807,26 @@ __global__ void k_point_span(const int* pt_ptr, const int* obs_img, int P, int* 
   if (e > b) atomicMax(span_max, obs_img[e - 1] - obs_img[b]);
 }
 
+// The fused path ends in Sband: when the band is narrow enough for the register window of
+// k_band_chol, the reduced system never exists as a dense matrix.
+void setup_band_chol(psfm_ba_solver* S) {
+  const int nb = 6 * S->F;
+  const int bw = std::min(S->bw, nb - 1);
+  const int W = band_chol_window(bw);
+  S->band_chol = S->fused && W > 0 && !getenv("PSFM_OLD_CHOL");
+  if (!S->band_chol) {
+    S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), S->stream);
+    return;
+  }
+  S->bcW = W; S->bcBw = bw;
+  S->bcRows = band_chol_rows(nb, W);
+  S->d_Ab.alloc((size_t)S->bcRows * (W + 4), S->stream);
+  S->d_C4.alloc(16, S->stream);
+  S->d_Lr.alloc((size_t)nb * (bw + 1), S->stream); S->d_Lr.zero(S->stream);
+  S->d_La.alloc(4 * (size_t)nb, S->stream);
+  S->d_dinv.alloc(nb, S->stream);
+}
+
 // (i, j) observation pairs of every point grouped by image pair — built once per problem
 void ensure_pairs(psfm_ba_solver* S) {
   if (S->pairs_ready) return;
@@ -850,7 +877,8 @@ void ensure_pairs(psfm_ba_solver* S) {
     S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
     S->d_bandrep.alloc(S->band_n, st); S->d_bandrep.zero(st);
     S->d_xcamrep.alloc((size_t)NREP * F * NVX2, st); S->d_xcamrep.zero(st);
-    S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), st); S->d_cholfail.alloc(1, st);
+    S->d_cholfail.alloc(1, st);
+    setup_band_chol(S);
     PSFM_CUDA(cudaStreamSynchronize(st));
     S->pairs_ready = true;
     return;
@@ -928,7 +956,8 @@ void ensure_pairs(psfm_ba_solver* S) {
     S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
     S->d_bandrep.alloc(S->band_n * nrep, st); S->d_bandrep.zero(st);
     S->d_xcamrep.alloc((size_t)NREP * F * NVX2, st); S->d_xcamrep.zero(st);
-    S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), st); S->d_cholfail.alloc(1, st);
+    S->d_cholfail.alloc(1, st);
+    setup_band_chol(S);
     PSFM_CUDA(cudaStreamSynchronize(st));
     S->pairs_ready = true;
     tm.mark("tile pair tasks (explicit Schur, fused)");
@@ -986,19 +1015,28 @@ void ensure_pairs(psfm_ba_solver* S) {
   tm.mark("pair structure (explicit Schur)");
 }
 
-// blocked band(+arrow) Cholesky of d_S (rhs carried as the extra row) -> d_x; false on a bad pivot
-bool launch_cholesky(psfm_ba_solver* S) {
+// blocked band(+arrow) Cholesky of d_S (rhs carried as the extra row) -> d_x; d_cholfail[0] = 1 on a
+// bad pivot (read back with the step scalars at the end of compute_step: no host sync here)
+void launch_cholesky(psfm_ba_solver* S) {
   cudaStream_t st = S->stream;
   const int nbnd = 6 * S->F;
   const int bw = std::min(S->bw, nbnd);
   {
-    static int grid_limit = 0;
-    if (grid_limit == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
-      PSFM_CUDA(cudaGetDevice(&dev));
-      PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_blocked, 256, 0));
-      grid_limit = std::max(1, sms * std::min(per_sm, 1));
+    int dev = 0;
+    PSFM_CUDA(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::vector<int> grid_limit_by_dev;
+    int grid_limit = 0;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if ((int)grid_limit_by_dev.size() <= dev) grid_limit_by_dev.resize(dev + 1, 0);
+      if (grid_limit_by_dev[dev] == 0) {
+        int sms = 0, per_sm = 0;
+        PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_blocked, 256, 0));
+        grid_limit_by_dev[dev] = std::max(1, sms * std::min(per_sm, 1));
+      }
+      grid_limit = grid_limit_by_dev[dev];
     }
     CholArgs ca;
     ca.A = S->d_S.p; ca.ns = S->NS; ca.lda = S->NS + 1; ca.nb = nbnd; ca.bw = bw + 1; ca.x = S->d_x.p; ca.fail = S->d_cholfail.p;
@@ -1023,21 +1061,51 @@ bool launch_cholesky(psfm_ba_solver* S) {
     PSFM_LAUNCH_CHECK();
   }
   { cudaEvent_t e = S->events.get(); PSFM_CUDA(cudaEventRecord(e, st)); S->ev_chol.back().second = e; }
-  int fail = 0;
-  PSFM_CUDA(cudaMemcpyAsync(&fail, S->d_cholfail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PSFM_CUDA(cudaStreamSynchronize(st));
   if (S->d_cholprof.n) {   // debugging aid: cumulative SM cycles of CTA 0 per phase
     unsigned long long h[8];
+    PSFM_CUDA(cudaStreamSynchronize(st));
     PSFM_CUDA(cudaMemcpy(h, S->d_cholprof.p, sizeof(h), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[psfm chol cycles] diag %llu rows %llu sync %llu trail %llu sync %llu backsub %llu\n",
             h[0], h[1], h[2], h[3], h[4], h[5]);
   }
-  return fail == 0;
+}
+
+// single-CTA register-window band Cholesky (ba_band_chol.cuh): assemble the compact band matrix,
+// factor, solve -> d_x; d_cholfail[0] = 1 on a bad pivot
+void launch_band_cholesky(psfm_ba_solver* S) {
+  cudaStream_t st = S->stream;
+  const int nb = 6 * S->F, W = S->bcW, bw = S->bcBw, RS = W + 4;
+  BandAsmArgs2 b;
+  b.Sband = S->d_xband.p + (size_t)S->F * NVX2;
+  b.lin_cam = S->d_lin.p; b.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
+  b.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
+  b.xcam = S->d_xband.p; b.xstride = NVX2;
+  b.scale_c = S->d_scale_c.p; b.Dc2 = S->d_Dc2.p; b.rhs = S->d_rhs.p; b.active = S->d_active.p;
+  b.F = S->F; b.span = S->span; b.nb = nb; b.bw = bw; b.W = W; b.RS = RS; b.nrows = S->bcRows;
+  b.Ab = S->d_Ab.p; b.C4 = S->d_C4.p;
+  k_band_assemble<<<grid_for((size_t)S->bcRows * RS), 256, 0, st>>>(b);
+  PSFM_LAUNCH_CHECK();
+  BandCholArgs c;
+  c.Ab = S->d_Ab.p; c.C4 = S->d_C4.p; c.nb = nb; c.bw = bw; c.W = W; c.RS = RS; c.ns = S->NS;
+  c.Lr = S->d_Lr.p; c.La = S->d_La.p; c.dinv = S->d_dinv.p; c.x = S->d_x.p; c.fail = S->d_cholfail.p;
+  static const bool want_prof = getenv("PSFM_CHOL_PROFILE") != nullptr;
+  if (want_prof && S->d_cholprof.n < 16) { S->d_cholprof.alloc(16, st); S->d_cholprof.zero(st); }
+  c.prof = want_prof ? reinterpret_cast<long long*>(S->d_cholprof.p) : nullptr;
+  band_chol_launch(c, st);
+  if (want_prof) {
+    long long h[4];
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    PSFM_CUDA(cudaMemcpy(h, S->d_cholprof.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const double np_ = (double)std::max(1ll, h[3]);
+    fprintf(stderr, "[psfm band chol cycles] factor %lld (%lld pivots, %.0f / pivot) corner+stage %lld backsub %lld\n", h[0], h[3],
+            (double)h[0] / np_, h[1], h[2]);
+  }
+  { cudaEvent_t e = S->events.get(); PSFM_CUDA(cudaEventRecord(e, st)); S->ev_chol.back().second = e; }
 }
 
 
-// exact reduced-system solve, fused tile path: k_schur_tile -> band blocks -> dense S -> Cholesky
-bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) {
+// exact reduced-system solve, fused tile path: k_schur_tile -> band blocks -> (band matrix | dense S) -> Cholesky
+void do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) {
   cudaStream_t st = S->stream;
   const size_t nx = (size_t)S->F * NVX2;
   StArgs w;
@@ -1066,6 +1134,7 @@ bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
   PSFM_LAUNCH_CHECK();
   dist::allreduce_sum(S->d_xband.p, S->d_xband.n, st);
   cam_finalize(S, c, radius, true);
+  if (S->band_chol) { launch_band_cholesky(S); return; }
   S->d_S.zero(st);
   BandAsmArgs ba_;
   ba_.Sband = S->d_xband.p + nx; ba_.scale_c = S->d_scale_c.p; ba_.F = S->F; ba_.span = S->span; ba_.lda = S->NS + 1; ba_.S = S->d_S.p;
@@ -1080,11 +1149,11 @@ bool do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
   k_schur_assemble_local<<<grid_for(S->F, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
-  return launch_cholesky(S);
+  launch_cholesky(S);
 }
 
-// exact reduced-system solve: explicit S, banded Cholesky; solution in d_x. returns false on failure
-bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
+// exact reduced-system solve: explicit S, banded Cholesky; solution in d_x (d_cholfail on failure)
+void do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   ensure_pairs(S);
   cudaStream_t st = S->stream;
   SwArgs w;
@@ -1121,7 +1190,7 @@ bool do_explicit_solve(psfm_ba_solver* S, const RunCfg& c) {
   dist::allreduce_sum(S->d_S.p, S->d_S.n, st);
   k_schur_assemble_global<<<grid_for(S->F + S->C, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
   k_schur_assemble_finish<<<grid_for(S->NS, 128), 128, 0, st>>>(a); PSFM_LAUNCH_CHECK();
-  return launch_cholesky(S);
+  launch_cholesky(S);
 }
 
 // LevenbergMarquardtStrategy::ComputeStep + ComputeCandidatePointAndEvaluateCost
@@ -1143,7 +1212,8 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   const bool fused = explicit_ok && S->fused;
   do_reduced_setup(S, c, radius, fused);
   if (explicit_ok) {
-    so.pcg_flag = (fused ? do_explicit_solve_fused(S, c, radius) : do_explicit_solve(S, c)) ? PCG_SUCCESS : PCG_FAILURE;
+    if (fused) do_explicit_solve_fused(S, c, radius); else do_explicit_solve(S, c);
+    so.pcg_flag = PCG_SUCCESS;     // the factorisation's verdict comes back with the step scalars below
     iters = 1;
   } else {
     so.pcg_flag = do_pcg(S, c, q_tol, r_tol, max_it, &iters, nprod);
@@ -1178,7 +1248,9 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   d2h(S, S->hs->step, S->d_step.p, 4);
   d2h(S, S->hs->rep, S->d_rep.p, 2);
   d2h(S, &S->hs->prep_fail, S->d_prep.p + (size_t)S->F * NVL + (size_t)S->C * NVI, 1);
+  if (explicit_ok) d2h(S, &S->hs->chol_fail, S->d_cholfail.p, 1);
   PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  if (explicit_ok && S->hs->chol_fail) so.pcg_flag = PCG_FAILURE;
   so.linear_ok = (so.pcg_flag != PCG_FAILURE) && !(S->hs->prep_fail > 0.0);
   so.mcc = -S->hs->step[0];
   so.step_sq = S->hs->step[1] + S->hs->rep[0];
@@ -1531,6 +1603,47 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
       for (size_t id = 0; id < P; ++id)
         for (int k = 0; k < 3; ++k) gradient_pts[3 * (size_t)S->pt_orig[id] + k] = gp[k * P + id];
     }
+    return PSFM_OK;
+  } catch (const CudaFail& f) {
+    return f.code;
+  }
+}
+
+extern "C" int psfm_ba_band_solve(const double* A, const double* b, int32_t nb, int32_t bw, double* x) {
+  if (!A || !b || !x || nb < 1 || bw < 0) return PSFM_ERR_INVALID;
+  int rc = check_device();
+  if (rc != PSFM_OK) return rc;
+  bw = std::min(bw, nb - 1);
+  const int W = band_chol_window(bw), RS = W + 4, n = nb + 3;
+  if (W == 0) { set_error("psfm_ba_band_solve: band too wide for the register window"); return PSFM_ERR_UNSUPPORTED; }
+  const int nrows = band_chol_rows(nb, W);
+  std::vector<double> Ab((size_t)nrows * RS, 0.0), C4(16, 0.0);
+  for (int r = 0; r < nrows; ++r) {
+    double* row = &Ab[(size_t)r * RS];
+    if (r >= nb) { row[0] = 1.0; continue; }
+    for (int k = 0; k <= std::min(bw, r); ++k) row[k] = A[(size_t)r * n + (r - k)];
+    for (int a = 0; a < 3; ++a) row[W + a] = A[(size_t)(nb + a) * n + r];
+    row[W + 3] = b[r];
+  }
+  for (int a = 0; a < 3; ++a) {
+    for (int c = 0; c < 3; ++c) C4[4 * a + c] = A[(size_t)(nb + a) * n + nb + c];
+    C4[12 + a] = C4[4 * a + 3] = b[nb + a];
+  }
+  try {
+    cudaStream_t st = nullptr;
+    DBuf<double> dAb, dC4, dLr, dLa, dinv, dx;
+    DBuf<int> dfail;
+    dAb.alloc(Ab.size()); dC4.alloc(16); dLr.alloc((size_t)nb * (bw + 1)); dLa.alloc(4 * (size_t)nb); dinv.alloc(nb); dx.alloc(n); dfail.alloc(1);
+    dAb.upload(Ab.data(), Ab.size(), st); dC4.upload(C4.data(), 16, st); dLr.zero(st);
+    BandCholArgs c;
+    c.Ab = dAb.p; c.C4 = dC4.p; c.nb = nb; c.bw = bw; c.W = W; c.RS = RS; c.ns = n;
+    c.Lr = dLr.p; c.La = dLa.p; c.dinv = dinv.p; c.x = dx.p; c.fail = dfail.p;
+    c.prof = nullptr;
+    band_chol_launch(c, st);
+    int fail = 0;
+    PSFM_CUDA(cudaMemcpy(&fail, dfail.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (fail) { set_error("psfm_ba_band_solve: matrix is not positive definite"); return PSFM_ERR_INVALID; }
+    PSFM_CUDA(cudaMemcpy(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return PSFM_OK;
   } catch (const CudaFail& f) {
     return f.code;

@@ -169,3 +169,21 @@ def test_matches_scipy_optimum_trivial_loss():
     x0 = np.concatenate([prob.tvec[tm], prob.xyz.ravel()])
     ref = scipy.optimize.least_squares(fun, x0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12)
     assert abs(s.final_cost - ref.cost) <= 1e-7 * ref.cost
+
+
+def test_block_sparse_schur_matches_dense_assembly(monkeypatch):
+    """The SPARSE_SCHUR restatement (oracle/ba_schur_blocks.h: block-sparse S, band + arrow
+    Cholesky) against the general dense assembly + dense Cholesky, on a banded (video) and on a
+    dense co-visibility pattern, pass A and pass B."""
+    for (F, P, L, rng) in ((40, 1200, 5, None), (14, 500, 6, (2, 14))):
+        prob, _ = syn.make_ba_problem(F, P, L, seed=21, track_len_range=rng)
+        for rot, focal in ((False, False), (True, True)):
+            o = oracle.ba_global_options(refine_rotation=rot, refine_focal_length=focal)
+            o.linear_solver = _abi.SOLVER_EXACT_SCHUR
+            monkeypatch.delenv("PSFM_ORACLE_DENSE_SCHUR", raising=False)
+            sc0, sp0, _ = oracle.ba_linear_step(prob, o, 1e3, _abi.SOLVER_EXACT_SCHUR)
+            monkeypatch.setenv("PSFM_ORACLE_DENSE_SCHUR", "1")
+            sc1, sp1, _ = oracle.ba_linear_step(prob, o, 1e3, _abi.SOLVER_EXACT_SCHUR)
+            monkeypatch.delenv("PSFM_ORACLE_DENSE_SCHUR", raising=False)
+            assert np.abs(sc0 - sc1).max() <= 1e-9 * np.abs(sc1).max()
+            assert np.abs(sp0 - sp1).max() <= 1e-9 * np.abs(sp1).max()
