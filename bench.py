@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native ParticleSfM hot paths.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2..5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one global bundle adjustment (HP2) of the BASELINE.json target workload
 — F=200 frames x P=500k trajectories x 12 observations/track, synthetic (SURVEY.md §8d
 "target config", seed 5) — from the perturbed start to the reference's termination
 criteria (GlobalBundleAdjustment options, controllers/global_mapper.cc:41-71, pass B:
-rotations + focal length refined).
+rotations + focal length refined).  `--config N` runs BASELINE.json's configs[N-1] stand-in
+ instead; the headline (no flag) stays the target config.
 
 `value`  = observations / second of solve = M / t_step, problem resident in HBM
            (observations, structure uploaded once; the state is re-set every step).
@@ -17,8 +18,10 @@ rotations + focal length refined).
            result — all inside the timed region.
 The line also carries the HP1 number (trajectory optimiser, pts/s) under "traj_opt".
 
-`--impl reference` times the CPU oracle port (the reference's algorithm choices: exact
-Schur, all host threads) on a bounded sample of the same workload.
+`--impl reference` times the CPU arm — the oracle's restatement of the reference's algorithm
+(Ceres LM + SPARSE_SCHUR: block-sparse Schur complement, band Cholesky; OpenMP over all host
+threads, min(ncpu, 64) as sfm/main_sfm.py:144) — on the SAME workload, full size; the sample
+is only shrunk (and said so) when a full-size solve would not fit the driver's time budget.
 """
 import argparse
 import ctypes as C
@@ -35,9 +38,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(num_images=200, num_points=500_000, track_len=12, seed=5)
-CPU_SAMPLE_POINTS = 50_000
-TRAJ = dict(num=111_616, height=436, width=1024, seed=1)   # Sintel alley_1 @ sample_ratio 2
+# BASELINE.json configs / SURVEY.md §8(d) stand-ins.  "target" is the headline.
+CONFIGS = {
+    "target": dict(name="target: 200 frames x 500k trajectories x 12 obs/track",
+                   ba=dict(num_images=200, num_points=500_000, track_len=12, seed=5),
+                   traj=dict(num=111_616, height=436, width=1024, seed=1, label="Sintel alley_1 shape 1024x436, sample_ratio 2")),
+    "2": dict(name="config 2 stand-in: Sintel alley_1 shape, F=50, P=3e5, track length U{3..50} (dense reduced system)",
+              ba=dict(num_images=50, num_points=300_000, track_len=12, track_len_range=(3, 50), seed=1),
+              traj=dict(num=111_616, height=436, width=1024, seed=1, label="Sintel alley_1 shape 1024x436, sample_ratio 2")),
+    "3": dict(name="config 3 stand-in: DAVIS shape, F=80, P=8e5, L=12, 30% of the observations dynamic and dropped",
+              ba=dict(num_images=80, num_points=800_000, track_len=12, dynamic_fraction=0.3, seed=2),
+              traj=dict(num=409_920, height=480, width=854, seed=2, label="DAVIS shape 854x480, sample_ratio 1")),
+    "4": dict(name="config 4 stand-in: ScanNet shape, F=300, P=2e5, L=15, 1 px noise (4 GPUs in BASELINE.json)",
+              ba=dict(num_images=300, num_points=200_000, track_len=15, noise_px=1.0, seed=3),
+              traj=dict(num=76_800, height=480, width=640, seed=3, label="ScanNet shape 640x480, sample_ratio 2")),
+    "5": dict(name="config 5: 500 frames x 2M trajectories x 12 obs/track (8 GPUs in BASELINE.json)",
+              ba=dict(num_images=500, num_points=2_000_000, track_len=12, seed=4),
+              traj=None),
+}
+REFERENCE_BUDGET_S = 240.0       # wall budget of one `--impl reference` run (all its steps)
 
 
 def read_peaks():
@@ -114,38 +133,85 @@ def global_pass_b_options(abi, lib, solver):
     return o
 
 
-def run_reference(args, rank):
-    """CPU arm: the oracle port (exact Schur = what the reference picks for F <= 1000,
-    bundle_adjustment.cc:276-286) on all host threads, bounded sample."""
+def workload_text(w, M):
+    extra = ""
+    if w.get("track_len_range"):
+        extra = f", track length U{{{w['track_len_range'][0]}..{w['track_len_range'][1]}}}"
+    if w.get("dynamic_fraction"):
+        extra += f", {int(100 * w['dynamic_fraction'])}% of the observations dropped as dynamic"
+    return (f"global BA pass B (rotation+translation+focal+points), F={w['num_images']} frames x P={w['num_points']} "
+            f"trajectories x L={w['track_len']} obs/track{extra}, M={M} observations, seed {w['seed']}")
+
+
+def cpu_solve_once(w, num_threads=0):
+    """One solve of the CPU arm on workload w; returns (seconds, summary, problem size M, threads)."""
+    import oracle
+    from particlesfm_b200 import synthetic as syn, _abi
+    prob, _ = syn.make_ba_problem(**w)
+    o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
+    o.linear_solver = _abi.SOLVER_AUTO
+    t0 = time.perf_counter()
+    s = oracle.ba_solve(prob, o, num_threads=num_threads)
+    return time.perf_counter() - t0, s, prob.num_observations, cpu_threads()
+
+
+def cpu_threads():
+    import oracle
+    return min(oracle.num_threads(), 64)      # ctx_init: min(cpu_count, 64), sfm/main_sfm.py:144
+
+
+def run_reference(args, rank, cfg):
+    """CPU arm: the oracle's restatement of the reference's path (LM + SPARSE_SCHUR for
+    50 < F <= 1000, bundle_adjustment.cc:276-286) on all host threads, same workload."""
     if rank != 0:
         return
     import oracle
     from particlesfm_b200 import synthetic as syn, _abi
-    w = dict(WORKLOAD)
-    w["num_points"] = args.cpu_points
+    w = dict(cfg["ba"])
+    if args.points:
+        w["num_points"] = args.points
+    full_points = w["num_points"]
     prob, _ = syn.make_ba_problem(**w)
     o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
     o.linear_solver = _abi.SOLVER_AUTO
+    # first warm-up solve at full size decides whether the whole run fits the budget
+    t0 = time.perf_counter()
+    oracle.ba_solve(prob.copy(), o)
+    t_full = time.perf_counter() - t0
+    total_solves = args.warmup + args.steps
+    shrunk = False
+    if t_full * (total_solves - 1) > REFERENCE_BUDGET_S:
+        frac = REFERENCE_BUDGET_S / (t_full * (total_solves - 1))
+        w["num_points"] = max(1000, int(full_points * frac))
+        prob, _ = syn.make_ba_problem(**w)
+        shrunk = True
     M = prob.num_observations
     times, iters = [], 0
-    for k in range(args.warmup + args.steps):
+    warm_rest = args.warmup if shrunk else max(0, args.warmup - 1)      # the probe solve was the first warm-up
+    for k in range(warm_rest + args.steps):
         p = prob.copy()
         t0 = time.perf_counter()
         s = oracle.ba_solve(p, o)
         dt = time.perf_counter() - t0
-        if k >= args.warmup:
+        if k >= warm_rest:
             times.append(dt)
             iters += s.num_iterations
     total = sum(times)
     val = M * len(times) / total
-    cores = oracle.num_threads()
-    sample = f"F={w['num_images']} P={w['num_points']} L={w['track_len']} seed={w['seed']} (M={M}; 1/{WORKLOAD['num_points'] // w['num_points']} of the points)"
+    cores = cpu_threads()
+    sample = ("the full workload" if not shrunk else
+              f"P={w['num_points']} of {full_points} points (a full-size solve takes {t_full:.1f} s on this host: "
+              f"{total_solves} of them exceed the {REFERENCE_BUDGET_S:.0f} s budget)")
     line = {
         "impl": "reference", "metric": "global_ba_observations_per_sec", "value": val, "unit": "observations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "global BA pass B, 200 frames x 500k trajectories x 12 obs (bounded sample: " + sample + ")",
-                   "linear_solver": "exact Schur + dense Cholesky (reference rule for <= 1000 images)"},
+        "config": {"workload": workload_text(w, M),
+                   "options": "GlobalBundleAdjustment (SoftL1, f_tol 1e-6, g_tol 1, p_tol 1e-8, <=50 LM its)",
+                   "linear_solver": "exact step: block-sparse Schur complement + band Cholesky (SPARSE_SCHUR restatement, "
+                                    "reference rule for <= 1000 images)",
+                   "implementation": "oracle/ba_oracle.c (C + OpenMP, -O3 AVX2/FMA): the reference's algorithm restated — "
+                                     "Ceres/COLMAP cannot be built in this image (DESIGN.md §9)"},
         "lm_iterations_per_step": iters / len(times),
         "obs_iterations_per_sec": M * iters / total,
         "cpu_baseline": {"value": val, "unit": "observations/s", "cores": cores, "kind": "port", "sample": sample},
@@ -161,8 +227,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=WORKLOAD["num_points"], help="trajectories of the BA workload")
-    ap.add_argument("--cpu-points", type=int, default=CPU_SAMPLE_POINTS)
+    ap.add_argument("--config", default="target", choices=sorted(CONFIGS), help="BASELINE.json configs[N-1] stand-in (SURVEY.md 8d)")
+    ap.add_argument("--points", type=int, default=0, help="override the number of trajectories of the BA workload")
     ap.add_argument("--solver", default="auto", choices=["auto", "iterative", "exact"],
                     help="auto = the reference rule (bundle_adjustment.cc:276-286): exact Schur for <= 1000 images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,8 +238,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, cfg)
         return
 
     from particlesfm_b200 import _abi, _lib, ba, synthetic as syn, traj
@@ -207,8 +274,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    w = dict(WORKLOAD)
-    w["num_points"] = args.points
+    w = dict(cfg["ba"])
+    if args.points:
+        w["num_points"] = args.points
     full, truth = syn.make_ba_problem(**w)
     M_total = full.num_observations
     prob = full.shard(rank, world)
@@ -248,44 +316,49 @@ def main():
     S.get_state()
     ate = syn.umeyama_ate(syn.camera_centres(prob.qvec, prob.tvec), truth["centres"])
 
-    # ---------------- roofline of the dominant kernel (live CUDA events) ----------------
-    # Algorithmic bytes per launch (factored-Jacobian formulation):
+    # ---------------- rooflines (live CUDA events of this run) ----------------
+    # HBM-bound kernels: algorithmic bytes per launch (factored-Jacobian formulation):
     #   Jacobian sweep      read xy 16 + idx 4, write D 24 + r 16; per point X 24 r, E'E/E'r 72 w
     #   implicit S*p        read D 24 + idx 4; per point X 24 + H~ 48
-    #   fused Schur tile    read D 24 + idx 4; per point 120; 4 B per pair entry; 8 B per task
-    #   (unfused fallback)  W / W H~: read 28, write 288, per point 120; pairs: 288 B/obs + 8 B/entry
+    # fp64-bound kernel: the fused Schur tile kernel does 108 fused multiply-adds per pair entry
+    #   (M = Q_i Jp_j' 12, T = M Jc_j 24, Jc_i' T 72) on operands held in shared memory; its HBM traffic
+    #   (D 24 + idx 4 per observation, 120 per point, 4 per pair entry) is reported beside it.
     peak, peak_src = read_peaks()
+    dfma = C.c_double()
+    dlat = C.c_double()
+    _lib.check(lib.psfm_measure_dfma(C.byref(dfma), C.byref(dlat)), "psfm_measure_dfma")
+    fp64_peak_tflops = 2e-12 * dfma.value
     M_local = prob.num_observations
-    L = w["track_len"]
-    pairs_local = M_local * (L + 1) / 2.0
+    Lmean = M_total / max(1, int(np.unique(full.obs_point).size))
     P_local = int(np.unique(prob.obs_point).size)
     n_expl = sum(s.num_explicit_solves for s in summaries)
     fused = bool(s_last.explicit_fused)
     kernels = {
-        "k_linearize (Jacobian sweep)": dict(ms=sum(s.linearize_ms for s in summaries), n=sum(s.num_linearize for s in summaries),
-                                             bytes=(20 + 40 + 96.0 / L) * M_local),
-        "k_schur_product (implicit S*p, one per PCG iteration)": dict(ms=sum(s.schur_product_ms for s in summaries),
+        "k_linearize (Jacobian sweep)": dict(bound="hbm", ms=sum(s.linearize_ms for s in summaries),
+                                             n=sum(s.num_linearize for s in summaries), bytes=(20 + 40 + 96.0 / Lmean) * M_local),
+        "k_schur_product (implicit S*p, one per PCG iteration)": dict(bound="hbm", ms=sum(s.schur_product_ms for s in summaries),
                                                                       n=sum(s.num_schur_products for s in summaries),
-                                                                      bytes=(28 + 72.0 / L) * M_local),
-        "k_schur_assemble + k_chol_blocked (reduced system solve)": dict(ms=sum(s.cholesky_ms for s in summaries), n=n_expl, bytes=None),
+                                                                      bytes=(28 + 72.0 / Lmean) * M_local),
+        "k_band_assemble + k_band_chol (reduced system: assemble, factor, solve; one CTA)": dict(
+            bound="latency", ms=sum(s.cholesky_ms for s in summaries), n=n_expl, bytes=None),
     }
     if fused:
-        # fused tile kernel: D 24 + idx 4 per observation, X/H~/G'E/w^ 120 per point, 4 B per pair entry,
-        # 8 B per (tile, image pair) task; W and W H~ never leave shared memory
         kernels["k_schur_tile (W, W H~ in shared memory + pair products, fused)"] = dict(
-            ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
+            bound="fp64", ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
+            flops=2.0 * (108.0 * s_last.num_pair_entries + 60.0 * M_local),
             bytes=28.0 * M_local + 120.0 * P_local + 4.0 * s_last.num_pair_entries + 8.0 * s_last.num_pair_tasks)
     else:
-        kernels["k_schur_w (W = Jc'Jp and W H~ per observation)"] = dict(ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
-                                                                         bytes=(28 + 288 + 120.0 / L) * M_local)
-        kernels["k_schur_pairs (image-pair blocks of the Schur complement)"] = dict(ms=sum(s.schur_pairs_ms for s in summaries), n=n_expl,
+        pairs_local = float(s_last.num_pair_entries)
+        kernels["k_schur_w (W = Jc'Jp and W H~ per observation)"] = dict(bound="hbm", ms=sum(s.schur_w_ms for s in summaries), n=n_expl,
+                                                                         bytes=(28 + 288 + 120.0 / Lmean) * M_local)
+        kernels["k_schur_pairs (image-pair blocks of the Schur complement)"] = dict(bound="hbm", ms=sum(s.schur_pairs_ms for s in summaries), n=n_expl,
                                                                                     bytes=288.0 * M_local + 8.0 * pairs_local)
 
-    # measured DRAM traffic per launch (ncu --set full capture of this workload at 1 GPU)
+    # measured DRAM traffic per launch (ncu --set full capture of the headline workload at 1 GPU, this round's kernels)
     traffic = {}
     try:
-        if world == 1 and args.points == WORKLOAD["num_points"]:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")) as f:
+        if world == 1 and args.config == "target" and not args.points:
+            with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
                 traffic = json.load(f)
     except (OSError, ValueError):
         traffic = {}
@@ -295,17 +368,24 @@ def main():
         if k["n"] == 0 or k["ms"] <= 0:
             return None
         avg = k["ms"] / k["n"]
-        d = {"kernel": name, "bound": "hbm", "avg_launch_ms": avg, "launches": k["n"], "share_of_step": k["ms"] / (1e3 * t_local),
-             "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": traffic.get(name.split(" ")[0])}
-        if k["bytes"]:
-            d["algorithmic_bytes_per_launch"] = k["bytes"]
-            d["achieved"] = k["bytes"] / (avg * 1e-3) / 1e9
+        d = {"kernel": name, "bound": k["bound"], "avg_launch_ms": avg, "launches": k["n"], "share_of_step": k["ms"] / (1e3 * t_local),
+             "traffic": traffic.get(name.split(" ")[0])}
+        if k["bound"] == "fp64":
+            d.update({"peak": fp64_peak_tflops, "unit": "TFLOP/s", "peak_source": "measured in this run (psfm_measure_dfma: chip-wide DFMA rate x 2)",
+                      "algorithmic_flops_per_launch": k["flops"], "achieved": k["flops"] / (avg * 1e-3) / 1e12})
+            d["frac"] = d["achieved"] / fp64_peak_tflops
+            d["hbm"] = {"algorithmic_bytes_per_launch": k["bytes"], "achieved_gbs": k["bytes"] / (avg * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": k["bytes"] / (avg * 1e-3) / 1e9 / peak}
+        elif k["bound"] == "hbm":
+            d.update({"peak": peak, "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_launch": k["bytes"],
+                      "achieved": k["bytes"] / (avg * 1e-3) / 1e9})
             d["frac"] = d["achieved"] / peak
         else:
-            d["achieved"], d["frac"] = None, None
+            d.update({"peak": None, "unit": None, "achieved": None, "frac": None,
+                      "note": "a chain of 6F dependent pivots in one CTA: bounded by the latency of one pivot step, not by bandwidth or flops"})
         return d
-    ranked = sorted((n for n in kernels if kernels[n]["bytes"] and kernels[n]["n"]), key=lambda n: -kernels[n]["ms"])
-    roofline = roof(ranked[0])
+    ranked = sorted((n for n in kernels if kernels[n]["bound"] != "latency" and kernels[n]["n"]), key=lambda n: -kernels[n]["ms"])
+    roofline = roof(ranked[0]) if ranked else None
     roofline_lin = roof("k_linearize (Jacobian sweep)")
     if roofline_lin:
         # SURVEY.md 8(d) defines the sweep's algorithmic bytes for the STORED-Jacobian formulation
@@ -349,11 +429,10 @@ def main():
         "metric": "global_ba_observations_per_sec", "value": value, "unit": "observations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"global BA pass B (rotation+translation+focal+points), F={w['num_images']} frames x "
-                               f"P={w['num_points']} trajectories x L={L} obs/track, M={M_total} observations, seed {w['seed']}",
+        "config": {"workload": workload_text(w, M_total), "baseline_config": cfg["name"],
                    "options": "GlobalBundleAdjustment (SoftL1, f_tol 1e-6, g_tol 1, p_tol 1e-8, <=50 LM its)",
                    "linear_solver": {2: "PCG on the reduced camera system, Schur-Jacobi, eta=0.1, <=100 its (Ceres ITERATIVE_SCHUR semantics)",
-                                     1: "exact step: explicit Schur complement + banded Cholesky on the device (reference rule for <= 1000 images)"}
+                                     1: "exact step: explicit Schur complement + band Cholesky on the device (reference rule for <= 1000 images)"}
                    [s_last.linear_solver_used],
                    "parallelism": f"points sharded over {world} GPU(s); NCCL all-reduce of the camera-side accumulators / reduced system",
                    "l2": "per-step working set (observations, linearisation, pair entries: ~0.7 GB) is larger than the 126 MB L2; no flush needed"},
@@ -366,43 +445,39 @@ def main():
                 "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "fp64_roof": {"dfma_per_s": dfma.value, "tflops": fp64_peak_tflops, "dependent_dfma_latency_cycles": dlat.value,
+                      "how": "psfm_measure_dfma: 8 independent DFMA chains per thread, 8 CTAs x 256 threads per SM, best of 4"},
         "roofline": roofline, "roofline_linearize": roofline_lin, "roofline_all_kernels": roofline_all,
     }
 
     # ---------------- HP1: trajectory optimiser, pts/s (rank 0, N = 1 shape) ----------------
-    if rank == 0 and not args.no_traj:
-        uv12, r1, r2, sc, f12 = syn.make_traj_inputs(TRAJ["num"], TRAJ["height"], TRAJ["width"], seed=TRAJ["seed"])
+    TR = cfg["traj"]
+    if rank == 0 and not args.no_traj and TR is not None:
+        uv12, r1, r2, sc, f12 = syn.make_traj_inputs(TR["num"], TR["height"], TR["width"], seed=TR["seed"])
         n = uv12.shape[0]
         ts, dev_ms = [], []
         for k in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            out, ssum = traj.optimize_location(uv12, r1, r2, sc, f12, n, TRAJ["width"], TRAJ["height"], return_summary=True)
+            out, ssum = traj.optimize_location(uv12, r1, r2, sc, f12, n, TR["width"], TR["height"], return_summary=True)
             if k >= args.warmup:
                 ts.append(time.perf_counter() - t0)
                 dev_ms.append(ssum.solve_ms)
-        traj_bytes = 104.0 * n + 8.0 * TRAJ["height"] * TRAJ["width"]
+        traj_bytes = 104.0 * n + 8.0 * TR["height"] * TR["width"]
         line["traj_opt"] = {"metric": "traj_opt_points_per_sec", "value_e2e": n / statistics.mean(ts),
                             "value_device": n / (statistics.mean(dev_ms) * 1e-3), "unit": "trajectories/s", "n": n,
-                            "iterations": ssum.num_iterations, "workload": "Sintel alley_1 shape 1024x436, sample_ratio 2",
+                            "iterations": ssum.num_iterations, "workload": TR["label"],
                             "roofline": {"bound": "hbm (latency-bound by design)", "achieved": traj_bytes / (statistics.mean(dev_ms) * 1e-3) / 1e9,
                                          "peak": peak, "unit": "GB/s", "frac": traj_bytes / (statistics.mean(dev_ms) * 1e-3) / 1e9 / peak}}
 
-    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only): ONE full-size solve ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
-        wc = dict(WORKLOAD)
-        wc["num_points"] = args.cpu_points
-        pc, _ = syn.make_ba_problem(**wc)
-        oc = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
-        oc.linear_solver = _abi.SOLVER_AUTO
-        t0 = time.perf_counter()
-        sc_ = oracle.ba_solve(pc, oc)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": pc.num_observations / dt, "unit": "observations/s", "cores": oracle.num_threads(),
+        dt, sc_, Mc, cores = cpu_solve_once(w)
+        line["cpu_baseline"] = {"value": Mc / dt, "unit": "observations/s", "cores": cores,
                                 "kind": "port", "lm_iterations": sc_.num_iterations,
-                                "sample": f"F={wc['num_images']} P={wc['num_points']} L={wc['track_len']} seed={wc['seed']} "
-                                          f"(M={pc.num_observations}), exact Schur + dense Cholesky, one solve to convergence ({dt:.1f} s)"}
-        if not args.no_traj:
+                                "sample": f"the full workload (M={Mc}), one solve to the same termination ({dt:.1f} s): oracle restatement of "
+                                          "LM + SPARSE_SCHUR (block-sparse Schur complement, band Cholesky), OpenMP"}
+        if not args.no_traj and TR is not None:
             t0 = time.perf_counter()
             _, so = oracle.traj_optimize(uv12, r1, r2, sc, f12, num_threads=8)
             line["traj_opt"]["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "trajectories/s", "cores": 8,

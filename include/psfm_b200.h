@@ -275,6 +275,60 @@ int psfm_ba_evaluate(psfm_ba_solver* s, const psfm_ba_options* opts, double* cos
 int psfm_ba_linear_step(psfm_ba_solver* s, const psfm_ba_options* opts, double radius,
                         double* step_cam, double* step_pts, int32_t* num_linear_iterations);
 
+/* ------------------------------------------------------------------------- */
+/* Refinement loop around the global BA, on the resident solver (the caller's  */
+/* observations stay in HBM; filters clear bits of an ALIVE mask and the tile   */
+/* structure is re-packed on the device).                                       */
+/*   IterativeGlobalRefinement   controllers/global_mapper.cc:245-271           */
+/*   AdjustGlobalBundle          sfm/global_mapper.cc:402-448                   */
+/*   filters / Normalize         base/reconstruction.cc:373-468,697-729,1321-1434 */
+/* All of them act on the solver's current state (psfm_ba_set_state / the       */
+/* result of the last psfm_ba_run).  Counts are the reference's num_filtered,   */
+/* summed over the ranks of a sharded problem.                                  */
+/* ------------------------------------------------------------------------- */
+#define PSFM_BA_MAX_REFINEMENTS 8
+
+typedef struct psfm_ba_refine_options {
+  int32_t max_refinements;          /* 5      ba_global_max_refinements */
+  double max_refinement_change;     /* 5e-4   ba_global_max_refinement_change */
+  double filter_max_reproj_error;   /* 4 px   Mapper filter_max_reproj_error */
+  double filter_min_tri_angle;      /* 1.5 deg */
+  double normalize_extent;          /* 10 */
+  double normalize_p0;              /* 0.1 */
+  double normalize_p1;              /* 0.9 */
+} psfm_ba_refine_options;
+
+typedef struct psfm_ba_refine_report {
+  int32_t num_rounds;
+  int32_t ba_iterations[PSFM_BA_MAX_REFINEMENTS];
+  int32_t ba_termination[PSFM_BA_MAX_REFINEMENTS];
+  int64_t num_observations[PSFM_BA_MAX_REFINEMENTS];     /* ComputeNumObservations() before the round */
+  int64_t num_negative_depth[PSFM_BA_MAX_REFINEMENTS];   /* FilterObservationsWithNegativeDepth */
+  int64_t num_changed[PSFM_BA_MAX_REFINEMENTS];          /* FilterAllPoints3D */
+  double changed[PSFM_BA_MAX_REFINEMENTS];               /* num_changed / num_observations */
+  double ba_final_cost[PSFM_BA_MAX_REFINEMENTS];
+  int64_t final_num_observations;
+  double total_time_in_seconds;
+} psfm_ba_refine_report;
+
+void psfm_ba_default_refine_options(psfm_ba_refine_options* r);
+/* Reconstruction::FilterObservationsWithNegativeDepth */
+int psfm_ba_filter_negative_depth(psfm_ba_solver* s, int64_t* num_filtered);
+/* Reconstruction::FilterAllPoints3D(max_reproj_error, min_tri_angle [deg]) */
+int psfm_ba_filter_points(psfm_ba_solver* s, double max_reproj_error, double min_tri_angle_deg, int64_t* num_filtered);
+/* Reconstruction::Normalize(extent, p0, p1, use_images = true); translation [3], scale may be NULL */
+int psfm_ba_normalize(psfm_ba_solver* s, double extent, double p0, double p1, double* translation, double* scale);
+/* observations still in the problem (all ranks) */
+int psfm_ba_num_observations(psfm_ba_solver* s, int64_t* num_alive);
+/* alive [M] over the caller's observations: 1 = still in the problem (this rank's shard) */
+int psfm_ba_get_observation_mask(psfm_ba_solver* s, uint8_t* alive);
+/* Point3D::Error() as the last point filter set it, [P], NaN where not set */
+int psfm_ba_get_point_errors(psfm_ba_solver* s, double* error);
+/* One IterativeGlobalRefinement pass with `opts` (GlobalBundleAdjustment options with the pass's
+   refine_* flags; the "< 10 images" tightening of AdjustGlobalBundle is applied inside). */
+int psfm_ba_iterative_refinement(psfm_ba_solver* s, const psfm_ba_options* opts, const psfm_ba_refine_options* ropts,
+                                 psfm_ba_refine_report* report);
+
 /* Measured fp64 roof of the current device (bench.py's roofline denominator for the kernels
    that are bounded by the fp64 FMA pipe rather than by HBM): sustained fused multiply-adds
    per second over the whole chip, and the latency in SM cycles of one dependent DFMA. */

@@ -87,8 +87,8 @@ def squared_reprojection_errors(prob):
     p = camera_points(prob)
     K = prob.cam_params[prob.image_camera[prob.obs_image]]
     with np.errstate(divide="ignore", invalid="ignore"):
-        u = K[:, 0] * p[:, 0] / p[:, 2] + K[:, 1] - prob.obs_xy[:, 0]
-        v = K[:, 0] * p[:, 1] / p[:, 2] + K[:, 2] - prob.obs_xy[:, 1]
+        u = K[:, 0] * (p[:, 0] / p[:, 2]) + K[:, 1] - prob.obs_xy[:, 0]     # WorldToImage(hnormalized())
+        v = K[:, 0] * (p[:, 1] / p[:, 2]) + K[:, 2] - prob.obs_xy[:, 1]
         e = u * u + v * v
     return np.where(p[:, 2] < EPS, DBL_MAX, e)
 

@@ -145,6 +145,42 @@ class BASummary(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+MAX_REFINEMENTS = 8   # PSFM_BA_MAX_REFINEMENTS
+
+
+class BARefineOptions(C.Structure):
+    _fields_ = [
+        ("max_refinements", C.c_int32),
+        ("max_refinement_change", C.c_double),
+        ("filter_max_reproj_error", C.c_double),
+        ("filter_min_tri_angle", C.c_double),
+        ("normalize_extent", C.c_double),
+        ("normalize_p0", C.c_double),
+        ("normalize_p1", C.c_double),
+    ]
+
+
+class BARefineReport(C.Structure):
+    _fields_ = [
+        ("num_rounds", C.c_int32),
+        ("ba_iterations", C.c_int32 * MAX_REFINEMENTS),
+        ("ba_termination", C.c_int32 * MAX_REFINEMENTS),
+        ("num_observations", C.c_int64 * MAX_REFINEMENTS),
+        ("num_negative_depth", C.c_int64 * MAX_REFINEMENTS),
+        ("num_changed", C.c_int64 * MAX_REFINEMENTS),
+        ("changed", C.c_double * MAX_REFINEMENTS),
+        ("ba_final_cost", C.c_double * MAX_REFINEMENTS),
+        ("final_num_observations", C.c_int64),
+        ("total_time_in_seconds", C.c_double),
+    ]
+
+    def rounds(self):
+        return [dict(num_observations=self.num_observations[i], num_negative_depth=self.num_negative_depth[i],
+                     changed_observations=self.num_changed[i], changed=self.changed[i],
+                     ba_iterations=self.ba_iterations[i], final_cost=self.ba_final_cost[i],
+                     termination=self.ba_termination[i]) for i in range(self.num_rounds)]
+
+
 def _ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
 

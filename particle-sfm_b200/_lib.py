@@ -17,7 +17,9 @@ EXPORTS = [
     "psfm_traj_default_options", "psfm_traj_optimize", "psfm_traj_optimize_device",
     "psfm_ba_default_options", "psfm_ba_global_options", "psfm_ba_solve", "psfm_ba_create",
     "psfm_ba_set_state", "psfm_ba_run", "psfm_ba_get_state", "psfm_ba_destroy", "psfm_ba_evaluate",
-    "psfm_ba_linear_step", "psfm_ba_band_solve", "psfm_measure_dfma", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
+    "psfm_ba_linear_step", "psfm_ba_band_solve", "psfm_measure_dfma", "psfm_ba_default_refine_options",
+    "psfm_ba_filter_negative_depth", "psfm_ba_filter_points", "psfm_ba_normalize", "psfm_ba_num_observations",
+    "psfm_ba_get_observation_mask", "psfm_ba_get_point_errors", "psfm_ba_iterative_refinement", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
     "psfm_dist_rank", "psfm_dist_finalize",
 ]
 
@@ -59,6 +61,17 @@ def lib():
     L.psfm_ba_evaluate.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), dp, dp, dp, dp]
     L.psfm_ba_linear_step.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), C.c_double, dp, dp, ip]
     L.psfm_measure_dfma.argtypes = [dp, dp]
+    i64p = C.POINTER(C.c_int64)
+    L.psfm_ba_default_refine_options.argtypes = [C.POINTER(_abi.BARefineOptions)]
+    L.psfm_ba_default_refine_options.restype = None
+    L.psfm_ba_filter_negative_depth.argtypes = [C.c_void_p, i64p]
+    L.psfm_ba_filter_points.argtypes = [C.c_void_p, C.c_double, C.c_double, i64p]
+    L.psfm_ba_normalize.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.psfm_ba_num_observations.argtypes = [C.c_void_p, i64p]
+    L.psfm_ba_get_observation_mask.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
+    L.psfm_ba_get_point_errors.argtypes = [C.c_void_p, dp]
+    L.psfm_ba_iterative_refinement.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), C.POINTER(_abi.BARefineOptions),
+                                               C.POINTER(_abi.BARefineReport)]
     L.psfm_ba_band_solve.argtypes = [dp, dp, C.c_int32, C.c_int32, dp]
     L.psfm_dist_get_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.psfm_dist_init.argtypes = [C.POINTER(C.c_uint8), C.c_int32, C.c_int32]

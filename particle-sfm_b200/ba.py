@@ -200,24 +200,67 @@ class Reconstruction:
     with their 2D observations, 3D points (base/reconstruction.h).  Same field names as
     sfm/colmap_utils/read_write_model.py so that models read from disk plug in."""
 
-    def __init__(self, cameras=None, images=None, points3D=None):
+    def __init__(self, cameras=None, images=None, points3D=None, reg_image_ids=None):
         self.cameras, self.images, self.points3D = cameras or {}, images or {}, points3D or {}
+        # reg_image_ids_ is REGISTRATION order in the reference (base/reconstruction.h); a model read
+        # from disk registers its images in file order (ReadImagesBinary, reconstruction.cc:1733-1790).
+        # The gauge of the global BA fixes reg[0] and reg[1] (sfm/global_mapper.cc:431-435), so the
+        # order is part of the result.  Default: insertion order of `images`.
+        self.reg_image_ids = list(reg_image_ids) if reg_image_ids is not None else None
 
     def RegImageIds(self):
-        return sorted(self.images.keys())
+        if self.reg_image_ids is not None:
+            return [i for i in self.reg_image_ids if i in self.images]
+        return list(self.images.keys())
+
+    def NumRegImages(self):
+        return len(self.RegImageIds())
+
+    def ComputeNumObservations(self):
+        """base/reconstruction.cc:756-762."""
+        return int(sum(np.count_nonzero(self.images[i].point3D_ids >= 0) for i in self.RegImageIds()
+                       if self.images[i].point3D_ids is not None))
+
+    def DeletePoint3D(self, point3D_id):
+        """base/reconstruction.cc:279-298: reset every Point2D of the track, erase the point."""
+        p = self.points3D.pop(point3D_id, None)
+        if p is None:
+            return
+        if p.image_ids is not None and len(p.image_ids):
+            for iid, j in zip(p.image_ids, p.point2D_idxs):
+                im = self.images.get(int(iid))
+                if im is not None and im.point3D_ids is not None and im.point3D_ids[int(j)] == point3D_id:
+                    im.point3D_ids[int(j)] = -1
+        else:                                   # container built without tracks: search
+            for im in self.images.values():
+                if im.point3D_ids is not None:
+                    im.point3D_ids[im.point3D_ids == point3D_id] = -1
+
+    def DeleteObservation(self, image_id, point2D_idx):
+        """base/reconstruction.cc:300-320: the whole point goes once its track length is <= 2;
+        otherwise the track element is removed and the Point2D reset."""
+        im = self.images[image_id]
+        pid = int(im.point3D_ids[point2D_idx])
+        p = self.points3D[pid]
+        length = len(p.image_ids) if p.image_ids is not None else self._track_length(pid)
+        if length <= 2:
+            self.DeletePoint3D(pid)
+            return
+        if p.image_ids is not None:
+            keep = ~((p.image_ids == image_id) & (p.point2D_idxs == point2D_idx))
+            p.image_ids, p.point2D_idxs = p.image_ids[keep], p.point2D_idxs[keep]
+        im.point3D_ids[point2D_idx] = -1
+
+    def _track_length(self, point3D_id):
+        return int(sum(np.count_nonzero(im.point3D_ids == point3D_id) for im in self.images.values()
+                       if im.point3D_ids is not None))
 
     def FilterObservationsWithNegativeDepth(self):
-        """base/reconstruction.cc:711-729: delete every observation whose point is not in
-        front of the camera (HasPointPositiveDepth: P.row(2)·[X;1] >= eps).  As in
-        Reconstruction::DeleteObservation, a point whose track would drop below 2
-        observations is deleted with all its observations."""
+        """base/reconstruction.cc:711-729: DeleteObservation for every Point2D whose point is not in
+        front of its camera (HasPointPositiveDepth: P.row(2) . [X; 1] >= eps), images in registration
+        order.  Returns the number of DeleteObservation calls, like the reference."""
         from .synthetic import qvec_to_rotmat
         eps = np.finfo(np.float64).eps
-        track_len = {}
-        for im in self.images.values():
-            if im.point3D_ids is not None:
-                for p in im.point3D_ids[im.point3D_ids >= 0]:
-                    track_len[int(p)] = track_len.get(int(p), 0) + 1
         n = 0
         for i in self.RegImageIds():
             im = self.images[i]
@@ -227,19 +270,11 @@ class Reconstruction:
             for j in np.nonzero(im.point3D_ids >= 0)[0]:
                 pid = int(im.point3D_ids[j])
                 if pid < 0 or pid not in self.points3D:
-                    continue
+                    continue                       # its point was deleted by an earlier call
                 if R[2] @ self.points3D[pid].xyz + im.tvec[2] >= eps:
                     continue
+                self.DeleteObservation(i, int(j))
                 n += 1
-                if track_len.get(pid, 0) <= 2:          # DeletePoint3D
-                    for other in self.images.values():
-                        if other.point3D_ids is not None:
-                            other.point3D_ids[other.point3D_ids == pid] = -1
-                    self.points3D.pop(pid, None)
-                    track_len.pop(pid, None)
-                else:
-                    im.point3D_ids[j] = -1
-                    track_len[pid] -= 1
         return n
 
     def Normalize(self, extent=10.0, p0=0.1, p1=0.9, use_images=True):
@@ -261,7 +296,10 @@ class Reconstruction:
         P0 = int(p0 * (n - 1)) if n > 3 else 0
         P1 = int(p1 * (n - 1)) if n > 3 else n - 1
         lo, hi = cs[P0].astype(np.float64), cs[P1].astype(np.float64)
-        mean = cs[P0:P1 + 1].astype(np.float64).sum(0) / (P1 - P0 + 1)
+        mean = np.zeros(3)
+        for k in range(P0, P1 + 1):                 # accumulated sequentially, as the reference does
+            mean += cs[k].astype(np.float64)
+        mean /= (P1 - P0 + 1)
         old_extent = np.linalg.norm(hi - lo)
         scale = 1.0 if old_extent < np.finfo(np.float64).eps else extent / old_extent
         R = qvec_to_rotmat(q)
@@ -275,7 +313,8 @@ class Reconstruction:
 def flatten(reconstruction, config):
     """BundleAdjuster::SetUp (bundle_adjustment.cc:326-447) as arrays: one observation per
     Point2D with a Point3D in an image of the config.  Returns (BAProblem, index maps)."""
-    image_ids = sorted(config.Images())
+    reg = reconstruction.RegImageIds()
+    image_ids = [i for i in reg if config.HasImage(i)] + sorted(i for i in config.Images() if i not in set(reg))
     cam_ids = sorted({reconstruction.images[i].camera_id for i in image_ids})
     cam_index = {c: k for k, c in enumerate(cam_ids)}
     for c in cam_ids:
@@ -284,12 +323,13 @@ def flatten(reconstruction, config):
                                  "features with --ImageReader.camera_model SIMPLE_PINHOLE)")
     pt_ids = sorted(reconstruction.points3D.keys())
     pt_index = {p: k for k, p in enumerate(pt_ids)}
-    obs_image, obs_point, obs_xy = [], [], []
+    obs_image, obs_point, obs_xy, obs_p2d = [], [], [], []
     for k, i in enumerate(image_ids):
         im = reconstruction.images[i]
         if im.point3D_ids is None:
             continue
         sel = np.nonzero(im.point3D_ids >= 0)[0]
+        obs_p2d.append(sel.astype(np.int64))
         obs_image.append(np.full(sel.shape[0], k, np.int32))
         obs_point.append(np.array([pt_index[int(p)] for p in im.point3D_ids[sel]], np.int32))
         obs_xy.append(np.asarray(im.xys, np.float64)[sel])
@@ -309,7 +349,31 @@ def flatten(reconstruction, config):
         cat(obs_image, (0,), np.int32), cat(obs_point, (0,), np.int32), cat(obs_xy, (0, 2), np.float64),
         np.array([cam_index[reconstruction.images[i].camera_id] for i in image_ids], np.int32),
         pose_constant, tmask, np.array([config.IsConstantCamera(c) for c in cam_ids], np.uint8))
-    return prob, dict(image_ids=image_ids, cam_ids=cam_ids, pt_ids=pt_ids)
+    return prob, dict(image_ids=image_ids, cam_ids=cam_ids, pt_ids=pt_ids,
+                      obs_point2D_idx=cat(obs_p2d, (0,), np.int64))
+
+
+def apply_observation_mask(problem, maps, reconstruction, alive, point_errors=None):
+    """Make the container agree with the solver's ALIVE mask (what the reference's filters did to
+    its Tracks / Point2Ds): dead observations lose their point, points without observations are
+    deleted, tracks are rebuilt from the survivors; Point3D::Error from the last point filter."""
+    image_ids, pt_ids = maps["image_ids"], maps["pt_ids"]
+    dead = np.nonzero(~alive)[0]
+    for m in dead:
+        im = reconstruction.images[image_ids[problem.obs_image[m]]]
+        im.point3D_ids[maps["obs_point2D_idx"][m]] = -1
+    tracks = {}
+    for m in np.nonzero(alive)[0]:
+        tracks.setdefault(int(problem.obs_point[m]), []).append((image_ids[problem.obs_image[m]], int(maps["obs_point2D_idx"][m])))
+    for k, pid in enumerate(pt_ids):
+        if k not in tracks:
+            reconstruction.points3D.pop(pid, None)
+            continue
+        p = reconstruction.points3D[pid]
+        p.image_ids = np.array([t[0] for t in tracks[k]], np.int32)
+        p.point2D_idxs = np.array([t[1] for t in tracks[k]], np.int32)
+        if point_errors is not None and not np.isnan(point_errors[k]):
+            p.error = float(point_errors[k])
 
 
 def scatter(problem, maps, reconstruction):
@@ -375,6 +439,50 @@ class ResidentSolver:
         _lib.check(_lib.lib().psfm_ba_linear_step(self._h, C.byref(options_struct), radius, _lib.dptr(sc),
                                                   _lib.dptr(sp), C.byref(it)), "psfm_ba_linear_step")
         return sc, sp, it.value
+
+    # ---- the refinement loop around the BA, on the resident problem (csrc/ba_refine.cuh) ----
+    def filter_negative_depth(self):
+        """Reconstruction::FilterObservationsWithNegativeDepth; returns num_filtered."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().psfm_ba_filter_negative_depth(self._h, C.byref(n)), "psfm_ba_filter_negative_depth")
+        return n.value
+
+    def filter_points(self, max_reproj_error=4.0, min_tri_angle=1.5):
+        """Reconstruction::FilterAllPoints3D; returns num_filtered."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().psfm_ba_filter_points(self._h, max_reproj_error, min_tri_angle, C.byref(n)),
+                   "psfm_ba_filter_points")
+        return n.value
+
+    def normalize(self, extent=10.0, p0=0.1, p1=0.9):
+        """Reconstruction::Normalize on the solver's state; returns (translation, scale)."""
+        t, s = np.zeros(3), C.c_double()
+        _lib.check(_lib.lib().psfm_ba_normalize(self._h, extent, p0, p1, _lib.dptr(t), C.byref(s)), "psfm_ba_normalize")
+        return t, s.value
+
+    def num_observations(self):
+        n = C.c_int64()
+        _lib.check(_lib.lib().psfm_ba_num_observations(self._h, C.byref(n)), "psfm_ba_num_observations")
+        return n.value
+
+    def observation_mask(self):
+        m = np.zeros(self.problem.num_observations, np.uint8)
+        _lib.check(_lib.lib().psfm_ba_get_observation_mask(self._h, m.ctypes.data_as(C.POINTER(C.c_uint8))),
+                   "psfm_ba_get_observation_mask")
+        return m.astype(bool)
+
+    def point_errors(self):
+        e = np.zeros(self.problem.num_points)
+        _lib.check(_lib.lib().psfm_ba_get_point_errors(self._h, _lib.dptr(e)), "psfm_ba_get_point_errors")
+        return e
+
+    def iterative_refinement(self, options_struct, refine_options=None):
+        """One IterativeGlobalRefinement pass (controllers/global_mapper.cc:245-271); returns the report."""
+        rep = _abi.BARefineReport()
+        ro = C.byref(refine_options) if refine_options is not None else None
+        _lib.check(_lib.lib().psfm_ba_iterative_refinement(self._h, C.byref(options_struct), ro, C.byref(rep)),
+                   "psfm_ba_iterative_refinement")
+        return rep
 
     def close(self):
         if self._h:
@@ -449,3 +557,60 @@ def adjust_global_bundle(reconstruction, force_update_rotation, ba_refine_focal_
         return False, ba.Summary()
     reconstruction.Normalize()
     return True, ba.Summary()
+
+
+def _global_ba_options(force_update_rotation, ba_refine_focal_length, ba_refine_principal_point, ba_refine_extra_params,
+                       ba_fix_prior_rotation, ba_global_max_num_iterations, quiet, linear_solver):
+    o = global_bundle_adjustment_options(ba_global_max_num_iterations)
+    if force_update_rotation:
+        o.refine_rotation = not ba_fix_prior_rotation
+        o.refine_focal_length = ba_refine_focal_length
+        o.refine_principal_point = ba_refine_principal_point
+        o.refine_extra_params = ba_refine_extra_params
+    if quiet:
+        o.print_summary = False
+        o.solver_options.minimizer_progress_to_stdout = False
+    o.solver_options.linear_solver = linear_solver
+    return o
+
+
+def iterative_global_refinement(reconstruction, force_update_rotation, ba_refine_focal_length=True,
+                                ba_refine_principal_point=False, ba_refine_extra_params=False,
+                                ba_fix_prior_rotation=False, ba_global_max_num_iterations=50,
+                                ba_global_max_refinements=5, ba_global_max_refinement_change=0.0005,
+                                filter_max_reproj_error=4.0, filter_min_tri_angle=1.5, quiet=True,
+                                linear_solver=_abi.SOLVER_AUTO):
+    """IterativeGlobalRefinement (controllers/global_mapper.cc:245-271) on a Reconstruction: the whole
+    loop — negative-depth filter, BA, Normalize, FilterAllPoints3D, <= 5 rounds — runs on the resident
+    device problem (psfm_ba_iterative_refinement); the container is updated once at the end.  The
+    IncrementalTriangulator steps of the reference (CompleteAndMergeTracks, Retriangulate) and
+    FilterImages are not part of this library.  Returns the BARefineReport."""
+    reg = reconstruction.RegImageIds()
+    if len(reg) < 2:
+        raise RuntimeError("At least two images must be registered for global bundle-adjustment")
+    o = _global_ba_options(force_update_rotation, ba_refine_focal_length, ba_refine_principal_point,
+                           ba_refine_extra_params, ba_fix_prior_rotation, ba_global_max_num_iterations, quiet,
+                           linear_solver)
+    cfg = BundleAdjustmentConfig()
+    for i in reg:
+        cfg.AddImage(i)
+    cfg.SetConstantPose(reg[0])            # fix 7 DoF (sfm/global_mapper.cc:431-435)
+    cfg.SetConstantTvec(reg[1], [0])
+    problem, maps = flatten(reconstruction, cfg)
+    ro = _abi.BARefineOptions()
+    _lib.lib().psfm_ba_default_refine_options(C.byref(ro))
+    ro.max_refinements = ba_global_max_refinements
+    ro.max_refinement_change = ba_global_max_refinement_change
+    ro.filter_max_reproj_error = filter_max_reproj_error
+    ro.filter_min_tri_angle = filter_min_tri_angle
+    S = ResidentSolver(problem)
+    try:
+        rep = S.iterative_refinement(o.to_struct(), ro)
+        S.get_state()
+        alive = S.observation_mask()
+        err = S.point_errors()
+    finally:
+        S.close()
+    scatter(problem, maps, reconstruction)
+    apply_observation_mask(problem, maps, reconstruction, alive, err)
+    return rep

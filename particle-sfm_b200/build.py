@@ -61,9 +61,11 @@ def build_library(force=False, verbose=False):
             print("[build]", " ".join(cmd), flush=True)
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-ldl"]
+        # link beside the target and rename: a gpurun snapshot taken meanwhile never sees a half-written library
+        cmd = [NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-o", LIB + ".tmp"] + objs + ["-ldl"]
         print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(LIB + ".tmp", LIB)
     return LIB
 
 
@@ -75,9 +77,10 @@ def build_pybind(force=False):
     if force or _stale(tgt, deps):
         cmd = [CXX, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
                "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", INCLUDE,
-               src, "-o", tgt, "-ldl"]
+               src, "-o", tgt + ".tmp", "-ldl"]
         print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(tgt + ".tmp", tgt)
     return tgt
 
 

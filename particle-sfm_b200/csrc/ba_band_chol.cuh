@@ -111,7 +111,8 @@ struct BandCholArgs {
   double* dinv;             // [nb]          pivots d[j], replaced by 1 / sqrt(d[j]) after the factorisation
   double* x;                // [ns]
   int* fail;
-  long long* prof;          // optional [4]: SM cycles of factorisation | corner + staging | back substitution, pivots
+  int flags;                // timing experiments (PSFM_CHOL_FLAGS; results invalid): 1 no output of L, 2 no reciprocal, 4 no publish, 8 barrier + pivot load only, 16 no row streaming
+  long long* prof;          // optional [8]: SM cycles of factorisation | corner + staging | back substitution, pivots
 };
 
 // bar.sync 0 from role-specific loops: every thread of the CTA executes the same NUMBER of
@@ -192,23 +193,33 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     const int e = tid - ldr0;
     const bool band = e < W, live = e < W + 4;
     const double* src = a.Ab + (size_t)W * RS + e;        // row W
-    int pos = band ? (e == 0 ? 0 : W - e) : e;            // (W - e) mod W
-    auto issue = [&](int slot) {
-      if (live) cp_async8(ring + slot * BC_CSM + pos, src);
-      cp_async_commit();
-      src += RS;
-      if (band && ++pos == W) pos = 0;
-    };
-    issue(0); issue(1); issue(2); issue(3);                // rows W .. W+3 (W is a multiple of 8)
+    int pos = band ? (e == 0 ? 0 : W - e) : e;            // (W - e) mod W: position of entry e of row W
+    // rows travel global -> register (4 pivots ahead) -> ring: plain loads, NOT cp.async — a pending
+    // LDGSTS is a pending shared-memory write, and bar.sync drains those (measured: ~600 cycles / pivot)
+    double rg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { rg[i] = live ? __ldg(src) : 0.0; src += RS; }
     int kk = e;                                            // (e - pj) mod W for band entries
+    const bool no_out = (a.flags & 1) != 0, no_ring = (a.flags & 16) != 0;
+    long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
     for (int j0 = 0; j0 < nsteps; j0 += UN) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int j = j0 + u;
-        issue((u + 4) & (BC_RING - 1));                    // row j + W + 4
-        asm volatile("cp.async.wait_group 4;\n" ::: "memory");   // row j + W has landed
+        if (!no_ring) {
+          if (live) ring[u * BC_CSM + pos] = rg[u & 3];      // row j + W -> slot u
+          rg[u & 3] = live ? __ldg(src) : 0.0;               // row j + W + 4
+        }
+        src += RS;
+        if (band && ++pos == W) pos = 0;
+        if (a.prof) { const long long t = clock64(); p_own += t - tlast; tlast = t; }
         bc_bar();
-        if (j < nb) {
+        if (a.prof) {
+          const double dd = colbuf[(u & 1) * BC_CSM];        // first use after the barrier: the wait shows up here
+          const long long t = clock64();
+          p_wait += t - tlast + (dd == 1.25e-300 ? 1 : 0); tlast = t;
+        }
+        if (j < nb && !no_out) {
           const double val = colbuf[(u & 1) * BC_CSM + e];
           if (band) {
             if (kk <= bw && j + kk < nb) a.Lr[(size_t)(j + kk) * LS + kk] = val;
@@ -220,24 +231,26 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
         if (band && --kk < 0) kk = W - 1;
       }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (a.prof && tid == ldr0) { a.prof[4] = p_own; a.prof[5] = p_wait; }
   } else {
     // ---- workers (and idle threads of the last worker warp: barriers only)
     const double* sP = colbuf + BS * P;
     const double* sQ = colbuf + BS * Q;
     const double* sD = colbuf;                             // + pj
     int Pj = 0;
+    long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
     for (int j0 = 0; j0 < nsteps; j0 += UN) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        constexpr int G = UN / BS;                         // pivot groups per body
         const int ij = u % BS;
         const int par = (u & 1) * BC_CSM, parn = ((u + 1) & 1) * BC_CSM, slot = u * BC_CSM;
+        if (a.prof) { const long long t = clock64(); p_own += t - tlast; tlast = t; }
         bc_bar();
         const double d = sD[par + u];
         bad |= !(d > 0.0 && d <= 1.7976931348623157e308);
-        if (worker) {
-          const double invd = bc_rcp(d);
+        if (a.prof) { const long long t = clock64(); p_wait += t - tlast + (bad ? 0 : 0); tlast = t; }
+        if (worker && !(a.flags & 8)) {
+          const double invd = (a.flags & 2) ? 1.0 - 1e-3 * d : bc_rcp(d);
           double cp[BS], tq[BS], np[BS], nq[BS];
 #pragma unroll
           for (int i = 0; i < BS; i += 2) {
@@ -266,7 +279,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
           int Pjn = Pj;
           if (ij == BS - 1) { Pjn = Pj + 1; if (Pjn == Wb) Pjn = 0; }
           double* cbn = colbuf + parn;
-          if (Q == Pjn) {
+          if (a.flags & 4) {
+          } else if (Q == Pjn) {
 #pragma unroll
             for (int i = 0; i < BS; i += 2) *reinterpret_cast<double2*>(cbn + BS * P + i) = make_double2(v[i][ijn], v[i + 1][ijn]);
           } else if (P == Pjn) {
@@ -277,14 +291,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
         } else if (ij == BS - 1) {
           if (++Pj == Wb) Pj = 0;
         }
-        (void)G;
       }
       sD += UN;
       if (sD == colbuf + W) sD = colbuf;
     }
+    if (a.prof && tid == 0) { a.prof[6] = p_own; a.prof[7] = p_wait; }
   }
   __syncthreads();
   const long long tk1 = a.prof ? clock64() : 0;
+  if (a.prof && tid == 0) { a.prof[0] = tk1 - tk0; a.prof[3] = nsteps; }
   if (bad) s_fail = 1;
   // 1 / sqrt(d): normalisation of the stored columns, applied while staging the back substitution
   for (int j = tid; j < nb; j += blockDim.x) a.dinv[j] = rsqrt(__ldcg(a.dinv + j));
@@ -406,7 +421,9 @@ inline int band_chol_window(int bw) {
 inline int band_chol_rows(int nb, int W) { return ((nb + 7) & ~7) + W + 8; }
 
 // one launch (4 x 4 register blocks)
-inline void band_chol_launch(const BandCholArgs& c, cudaStream_t st) {
+inline void band_chol_launch(BandCholArgs c, cudaStream_t st) {
+  static const int flags = getenv("PSFM_CHOL_FLAGS") ? atoi(getenv("PSFM_CHOL_FLAGS")) : 0;
+  c.flags = flags;
   const int threads = band_chol_threads(c.W, 4);
   const size_t smem = band_chol_smem(c.bw);
 #define PSFM_BC_GO(BSV, MT)                                                                                        \

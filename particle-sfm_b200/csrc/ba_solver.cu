@@ -19,6 +19,7 @@
 #include "ba_structure.cuh"
 #include "ba_schur_explicit.cuh"
 #include "ba_band_chol.cuh"
+#include "ba_refine.cuh"
 #include "dist.cuh"
 
 namespace psfm {
@@ -104,6 +105,16 @@ struct psfm_ba_solver {
   StreamHolder sh;
   int F = 0, P_total = 0, P = 0, M = 0, C = 0, NS = 0, NB = 0, T = 0, nseg = 0, tile = 256, maxL = 0;
   int cap_ns = 1, cap_np = 1;
+  // the caller's observations stay on the device for the life of the solver; `alive` marks the ones
+  // still in the problem (the filters of the refinement loop clear bits, rebuild_structure re-packs)
+  int M0 = 0;
+  long long num_alive = 0;
+  bool structure_dirty = false;
+  DBuf<int> d_in_img, d_in_pt;
+  DBuf<double2> d_in_xy;
+  DBuf<unsigned char> d_alive;
+  DBuf<double> d_pt_error;       // [P_total] Point3D::Error of the last point filter (NaN: not set)
+  DBuf<unsigned long long> d_count;
   // host structure / config
   std::vector<int> pt_orig;      // internal point -> caller's point id
   std::vector<int> obs_orig;     // sorted observation -> caller's observation index
@@ -208,12 +219,11 @@ void d2h_sync(cudaStream_t st, T* dst, const T* src, size_t n) {
 
 inline unsigned grid_for(size_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
 
-// Device-side flattening of the problem into tiles (ba_structure.cuh).
-int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
-  PhaseTimer tm;
+// Configuration and the caller's observations -> device (once per solver).
+int upload_problem(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   const int F = pb->num_images, Pt = pb->num_points, M = pb->num_observations, C = pb->num_cameras;
   if (F <= 0 || C <= 0 || Pt < 0 || M < 0) { set_error("psfm_ba_create: bad sizes"); return PSFM_ERR_INVALID; }
-  S->F = F; S->P_total = Pt; S->M = M; S->C = C; S->NS = 6 * F + 3 * C; S->NB = 2 * F + C;
+  S->F = F; S->P_total = Pt; S->M = M; S->M0 = M; S->num_alive = M; S->C = C; S->NS = 6 * F + 3 * C; S->NB = 2 * F + C;
   S->image_camera.assign(pb->image_camera, pb->image_camera + F);
   for (int i = 0; i < F; ++i)
     if (S->image_camera[i] < 0 || S->image_camera[i] >= C) { set_error("image_camera out of range"); return PSFM_ERR_INVALID; }
@@ -221,22 +231,56 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   if (pb->pose_constant) S->pose_constant.assign(pb->pose_constant, pb->pose_constant + F);
   if (pb->tvec_constant_mask) S->tvec_mask.assign(pb->tvec_constant_mask, pb->tvec_constant_mask + F);
   if (pb->camera_constant) S->camera_constant.assign(pb->camera_constant, pb->camera_constant + C);
-  S->img_has_obs.assign(F, 0); S->cam_has_obs.assign(C, 0);
   cudaStream_t st = S->stream;
   S->d_img_cam.alloc(F, st); S->d_img_cam.upload(S->image_camera.data(), F, st);
+  S->d_in_img.alloc(M, st); S->d_in_pt.alloc(M, st); S->d_in_xy.alloc(M, st); S->d_alive.alloc(M, st);
+  S->d_in_img.upload(pb->obs_image, M, st); S->d_in_pt.upload(pb->obs_point, M, st);
+  S->d_in_xy.upload(reinterpret_cast<const double2*>(pb->obs_xy), M, st);
+  PSFM_CUDA(cudaMemsetAsync(S->d_alive.p, 1, (size_t)(M ? M : 1), st));
+  S->d_count.alloc(1, st);
+  return PSFM_OK;
+}
 
-  // raw observations -> device
-  DBuf<int> in_img, in_pt, cnt, min_img, order, keys32, keys32_out, pt_new, cnt_sorted, idx, idx_out, tile_ns, bad;
-  DBuf<double2> in_xy;
+// Device-side flattening of the ALIVE observations into tiles (ba_structure.cuh).  Called at
+// creation and again whenever a filter removed observations: the observations are re-packed
+// from the resident arrays, nothing is uploaded again.
+int build_structure(psfm_ba_solver* S) {
+  PhaseTimer tm;
+  const int F = S->F, Pt = S->P_total, C = S->C;
+  cudaStream_t st = S->stream;
+  S->img_has_obs.assign(F, 0); S->cam_has_obs.assign(C, 0);
+  S->flags_world = 1;
+  DBuf<int> c_img, c_pt, sel, cnt, min_img, order, keys32, keys32_out, pt_new, cnt_sorted, idx, idx_out, tile_ns, bad;
+  DBuf<double2> c_xy;
   DBuf<unsigned long long> keys, keys_out;
   DBuf<unsigned char> has_obs, tmp;
-  in_img.alloc(M, st); in_pt.alloc(M, st); in_xy.alloc(M, st);
-  in_img.upload(pb->obs_image, M, st); in_pt.upload(pb->obs_point, M, st);
-  in_xy.upload(reinterpret_cast<const double2*>(pb->obs_xy), M, st);
+  int M = S->M0;
+  const int* in_img_p = S->d_in_img.p;
+  const int* in_pt_p = S->d_in_pt.p;
+  const double2* in_xy_p = S->d_in_xy.p;
+  if (S->num_alive != S->M0) {
+    // stream compaction of the alive observations (index select + gather)
+    DBuf<int> iota, nsel;
+    iota.alloc(S->M0, st); sel.alloc(S->M0, st); nsel.alloc(1, st);
+    k_st_iota<<<grid_for(S->M0), 256, 0, st>>>(iota.p, S->M0); PSFM_LAUNCH_CHECK();
+    size_t need = 0;
+    cub::DeviceSelect::Flagged(nullptr, need, iota.p, S->d_alive.p, sel.p, nsel.p, S->M0, st);
+    DBuf<unsigned char> t2; t2.alloc(need + 256, st);
+    cub::DeviceSelect::Flagged(t2.p, need, iota.p, S->d_alive.p, sel.p, nsel.p, S->M0, st);
+    int h_n = 0;
+    PSFM_CUDA(cudaMemcpyAsync(&h_n, nsel.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    M = h_n;
+    c_img.alloc(M, st); c_pt.alloc(M, st); c_xy.alloc(M, st);
+    if (M) { k_gather_alive<<<grid_for(M), 256, 0, st>>>(sel.p, M, S->d_in_img.p, S->d_in_pt.p, S->d_in_xy.p, c_img.p, c_pt.p, c_xy.p); PSFM_LAUNCH_CHECK(); }
+    in_img_p = c_img.p; in_pt_p = c_pt.p; in_xy_p = c_xy.p;
+    S->num_alive = M;
+  }
+  S->M = M;
   cnt.alloc(Pt, st); min_img.alloc(Pt, st); has_obs.alloc(F, st); bad.alloc(1, st);
   has_obs.zero(st); bad.zero(st);
   if (Pt) { k_st_init<<<grid_for(Pt), 256, 0, st>>>(cnt.p, min_img.p, Pt, F); PSFM_LAUNCH_CHECK(); }
-  if (M) { k_st_count<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, M, F, Pt, cnt.p, min_img.p, has_obs.p, bad.p); PSFM_LAUNCH_CHECK(); }
+  if (M) { k_st_count<<<grid_for(M), 256, 0, st>>>(in_img_p, in_pt_p, M, F, Pt, cnt.p, min_img.p, has_obs.p, bad.p); PSFM_LAUNCH_CHECK(); }
   // internal point order: observed points by (first image, id); unobserved (key F) last
   order.alloc(Pt, st); keys32.alloc(Pt, st); keys32_out.alloc(Pt, st); idx.alloc(std::max(Pt, M), st); idx_out.alloc(std::max(Pt, M), st);
   pt_new.alloc(Pt, st); cnt_sorted.alloc((size_t)Pt + 1, st);
@@ -280,11 +324,12 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   // the device while the host packs the tiles below (radix sort is stable => ties keep input order)
   S->d_obs_img.alloc(M, st); S->d_obs_pt.alloc(M, st); S->d_obs_xy.alloc(M, st); S->d_obs_orig.alloc(M, st);
   if (M) {
-    k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img.p, in_pt.p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
+    k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img_p, in_pt_p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
     need = tmp_bytes + 256;
     cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, idx.p, S->d_obs_orig.p, M, 0, 32 + pbits, st);
-    k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy.p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
+    k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy_p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
     PSFM_LAUNCH_CHECK();
+    if (sel.n) { k_compose_index<<<grid_for(M), 256, 0, st>>>(S->d_obs_orig.p, sel.p, M); PSFM_LAUNCH_CHECK(); }   // -> caller's index
   }
   for (int i = 0; i < F; ++i) if (h_has[i]) { S->img_has_obs[i] = 1; S->cam_has_obs[S->image_camera[i]] = 1; }
   int P = 0, maxL = 0;
@@ -372,6 +417,8 @@ int build_structure(psfm_ba_solver* S, const psfm_ba_problem* pb) {
 
 void alloc_work(psfm_ba_solver* S) {
   const size_t M = S->M, P = S->P, F = S->F, C = S->C, NS = S->NS;
+  if (S->hs) { g_pinned.release(S->hs, S->hs_bytes); S->hs = nullptr; }
+  if (S->pin_state) { g_pinned.release(S->pin_state, S->pin_state_bytes); S->pin_state = nullptr; }
   S->d_active.alloc(NS, S->stream);
   for (int k = 0; k < 2; ++k) { S->d_pose[k].alloc(8 * F, S->stream); S->d_X[k].alloc(3 * P, S->stream); S->d_K[k].alloc(3 * C, S->stream); }
   S->d_r.alloc(2 * M, S->stream); S->d_a.alloc(3 * M, S->stream);
@@ -1093,12 +1140,12 @@ void launch_band_cholesky(psfm_ba_solver* S) {
   c.prof = want_prof ? reinterpret_cast<long long*>(S->d_cholprof.p) : nullptr;
   band_chol_launch(c, st);
   if (want_prof) {
-    long long h[4];
+    long long h[8];
     PSFM_CUDA(cudaStreamSynchronize(st));
     PSFM_CUDA(cudaMemcpy(h, S->d_cholprof.p, sizeof(h), cudaMemcpyDeviceToHost));
     const double np_ = (double)std::max(1ll, h[3]);
-    fprintf(stderr, "[psfm band chol cycles] factor %lld (%lld pivots, %.0f / pivot) corner+stage %lld backsub %lld\n", h[0], h[3],
-            (double)h[0] / np_, h[1], h[2]);
+    fprintf(stderr, "[psfm band chol cycles] factor %lld (%lld pivots, %.0f / pivot) corner+stage %lld backsub %lld | per pivot own/wait: helper %.0f/%.0f worker0 %.0f/%.0f\n",
+            h[0], h[3], (double)h[0] / np_, h[1], h[2], h[4] / np_, h[5] / np_, h[6] / np_, h[7] / np_);
   }
   { cudaEvent_t e = S->events.get(); PSFM_CUDA(cudaEventRecord(e, st)); S->ev_chol.back().second = e; }
 }
@@ -1317,8 +1364,29 @@ void print_summary(const psfm_ba_summary& s) {
          std::sqrt(s.final_cost / s.num_residuals_reduced), tn[s.termination]);
 }
 
+// Re-pack the surviving observations (after a filter) on the device: new tiles, new pair structure;
+// the state of record moves through the caller-order scratch (a point keeps its id, its slot changes).
+void rebuild_structure(psfm_ba_solver* S) {
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  std::vector<double> xyz(3 * (size_t)S->P_total, 0.0);
+  scatter_points(S, xyz.data());
+  S->num_alive = -1;                       // unknown until the compaction has counted
+  const int rc = build_structure(S);
+  if (rc != PSFM_OK) throw CudaFail{rc};
+  S->pairs_ready = false; S->fused = false; S->band_chol = false;
+  alloc_work(S);
+  gather_points(S, xyz.data());
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  S->structure_dirty = false;
+}
+
+inline void ensure_structure(psfm_ba_solver* S) {
+  if (S->structure_dirty) rebuild_structure(S);
+}
+
 int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* out) {
   RunCfg c;
+  ensure_structure(S);
   sync_observed_flags(S);
   int rc = resolve_cfg(S, opts, c);
   if (rc != PSFM_OK) return rc;
@@ -1500,7 +1568,8 @@ extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
   try {
     PSFM_CUDA(cudaStreamCreateWithFlags(&S->sh.s, cudaStreamNonBlocking));
     S->stream = S->sh.s;
-    rc = build_structure(S, pb);
+    rc = upload_problem(S, pb);
+    if (rc == PSFM_OK) rc = build_structure(S);
     if (rc != PSFM_OK) { delete S; return rc; }
     S->h_qvec.assign(pb->qvec, pb->qvec + 4 * (size_t)S->F);
     S->h_tvec.assign(pb->tvec, pb->tvec + 3 * (size_t)S->F);
@@ -1571,10 +1640,11 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
   if (!S) return PSFM_ERR_INVALID;
   try {
     RunCfg c;
+    ensure_structure(S);
     sync_observed_flags(S);
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
-      upload_state(S);
+    upload_state(S);
     set_masks_and_unit_scale(S, c);
     do_linearize(S, c, false);
     const size_t F = S->F, C = S->C, M = S->M, P = S->P;
@@ -1586,6 +1656,7 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
     if (P) d2h(S, gp.data(), S->d_gp.p, 3 * P);
     PSFM_CUDA(cudaStreamSynchronize(S->stream));
     if (cost) *cost = lin[F * NVL + C * NVI];
+    if (residuals) memset(residuals, 0, sizeof(double) * 2 * (size_t)S->M0);      // filtered observations: 0
     if (residuals)
       for (size_t j = 0; j < M; ++j) {
         residuals[2 * (size_t)obs_orig[j]] = r[j];
@@ -1607,6 +1678,242 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
   } catch (const CudaFail& f) {
     return f.code;
   }
+}
+
+// ---------------------------------------------------------------- refinement loop around the BA
+
+namespace {
+
+FilterCtx filter_ctx(psfm_ba_solver* S) {
+  FilterCtx c;
+  c.pt_ptr = S->d_pt_ptr.p; c.obs_img = S->d_obs_img.p; c.obs_xy = S->d_obs_xy.p; c.obs_orig = S->d_obs_orig.p;
+  c.pt_orig = nullptr; c.img_cam = S->d_img_cam.p;
+  c.pose = S->d_pose[S->cur].p; c.X = S->d_X[S->cur].p; c.K = S->d_K[S->cur].p;
+  c.P = S->P; c.alive = S->d_alive.p; c.count = S->d_count.p;
+  return c;
+}
+
+// the reference's num_filtered, summed over the ranks
+long long read_filter_count(psfm_ba_solver* S) {
+  unsigned long long h = 0;
+  PSFM_CUDA(cudaMemcpyAsync(&h, S->d_count.p, sizeof(h), cudaMemcpyDeviceToHost, S->stream));
+  PSFM_CUDA(cudaStreamSynchronize(S->stream));
+  if (dist::world_size() > 1) {
+    k_fill<<<1, 32, 0, S->stream>>>(S->d_x2.p, (double)h, 1);
+    PSFM_LAUNCH_CHECK();
+    dist::allreduce_sum(S->d_x2.p, 1, S->stream);
+    d2h(S, &S->hs->x2, S->d_x2.p, 1);
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    h = (unsigned long long)(S->hs->x2 + 0.5);
+  }
+  return (long long)h;
+}
+
+long long filter_negative_depth_impl(psfm_ba_solver* S) {
+  ensure_structure(S);
+  upload_state(S);
+  S->d_count.zero(S->stream);
+  if (S->P) {
+    k_filter_negative_depth<<<grid_for(S->P, 128), 128, 0, S->stream>>>(filter_ctx(S));
+    PSFM_LAUNCH_CHECK();
+  }
+  const long long n = read_filter_count(S);
+  if (n > 0) S->structure_dirty = true;
+  return n;
+}
+
+long long filter_points_impl(psfm_ba_solver* S, double max_reproj_error, double min_tri_angle_deg) {
+  ensure_structure(S);
+  upload_state(S);
+  cudaStream_t st = S->stream;
+  if (S->d_pt_error.n != (size_t)S->P_total) {
+    S->d_pt_error.alloc(S->P_total, st);
+    if (S->P_total) { k_fill<<<grid_for(S->P_total), 256, 0, st>>>(S->d_pt_error.p, nan(""), (size_t)S->P_total); PSFM_LAUNCH_CHECK(); }
+  }
+  DBuf<double> centres;
+  DBuf<int> pt_orig;
+  centres.alloc(3 * (size_t)S->F, st);
+  pt_orig.alloc(S->P, st);
+  pt_orig.upload(S->pt_orig.data(), S->P, st);
+  k_proj_centres<<<grid_for(S->F, 128), 128, 0, st>>>(S->d_pose[S->cur].p, S->F, centres.p);
+  PSFM_LAUNCH_CHECK();
+  S->d_count.zero(st);
+  if (S->P) {
+    FilterCtx c = filter_ctx(S);
+    c.pt_orig = pt_orig.p;
+    k_filter_points<<<grid_for(S->P, 128), 128, 0, st>>>(c, centres.p, max_reproj_error * max_reproj_error,
+                                                        min_tri_angle_deg * 0.017453292519943295, S->d_pt_error.p);
+    PSFM_LAUNCH_CHECK();
+  }
+  const long long n = read_filter_count(S);
+  if (n > 0) S->structure_dirty = true;
+  return n;
+}
+
+// Reconstruction::Normalize(extent, p0, p1, use_images = true), base/reconstruction.cc:373-468, on
+// the state of record (host; every run uploads it): per-axis independently sorted FLOAT coordinates
+// of the projection centres, robust box [P0, P1], translation = mean of the sorted coordinates in
+// that range, scale = extent / |box diagonal|.
+void normalize_impl(psfm_ba_solver* S, double extent, double p0, double p1, double* translation, double* scale_out) {
+  ensure_structure(S);
+  const int F = S->F;
+  double mean[3] = {0, 0, 0}, scale = 1.0;
+  if (F >= 2) {
+    std::vector<double> cen(3 * (size_t)F), R(9 * (size_t)F);
+    std::vector<float> cx(F), cy(F), cz(F);
+    for (int i = 0; i < F; ++i) {
+      double* q = &S->h_qvec[4 * (size_t)i];
+      const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      if (n == 0.0) { q[0] = 1.0; q[1] = q[2] = q[3] = 0.0; } else for (int k = 0; k < 4; ++k) q[k] /= n;
+      double* r = &R[9 * (size_t)i];
+      const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+      r[0] = 1.0 - 2.0 * (q2 * q2 + q3 * q3); r[1] = 2.0 * (q1 * q2 - q0 * q3); r[2] = 2.0 * (q1 * q3 + q0 * q2);
+      r[3] = 2.0 * (q1 * q2 + q0 * q3); r[4] = 1.0 - 2.0 * (q1 * q1 + q3 * q3); r[5] = 2.0 * (q2 * q3 - q0 * q1);
+      r[6] = 2.0 * (q1 * q3 - q0 * q2); r[7] = 2.0 * (q2 * q3 + q0 * q1); r[8] = 1.0 - 2.0 * (q1 * q1 + q2 * q2);
+      const double* t = &S->h_tvec[3 * (size_t)i];
+      for (int k = 0; k < 3; ++k) cen[3 * (size_t)i + k] = -(r[k] * t[0] + r[3 + k] * t[1] + r[6 + k] * t[2]);
+      cx[i] = (float)cen[3 * (size_t)i]; cy[i] = (float)cen[3 * (size_t)i + 1]; cz[i] = (float)cen[3 * (size_t)i + 2];
+    }
+    std::sort(cx.begin(), cx.end()); std::sort(cy.begin(), cy.end()); std::sort(cz.begin(), cz.end());
+    const size_t n = (size_t)F;
+    const size_t P0 = (size_t)((n > 3) ? p0 * (double)(n - 1) : 0.0);
+    const size_t P1 = (size_t)((n > 3) ? p1 * (double)(n - 1) : (double)(n - 1));
+    for (size_t i = P0; i <= P1; ++i) { mean[0] += cx[i]; mean[1] += cy[i]; mean[2] += cz[i]; }
+    for (int k = 0; k < 3; ++k) mean[k] /= (double)(P1 - P0 + 1);
+    const double dx = (double)cx[P1] - (double)cx[P0], dy = (double)cy[P1] - (double)cy[P0], dz = (double)cz[P1] - (double)cz[P0];
+    const double old_extent = std::sqrt(dx * dx + dy * dy + dz * dz);
+    scale = (old_extent < 2.220446049250313e-16) ? 1.0 : extent / old_extent;
+    for (int i = 0; i < F; ++i) {
+      const double* r = &R[9 * (size_t)i];
+      double c[3];
+      for (int k = 0; k < 3; ++k) c[k] = -((cen[3 * (size_t)i + k] - mean[k]) * scale);
+      double* t = &S->h_tvec[3 * (size_t)i];
+      for (int k = 0; k < 3; ++k) t[k] = r[3 * k] * c[0] + r[3 * k + 1] * c[1] + r[3 * k + 2] * c[2];
+    }
+    double* X = S->pin_state + 8 * (size_t)F;
+    for (size_t id = 0; id < (size_t)S->P; ++id)
+      for (int k = 0; k < 3; ++k) X[3 * id + k] = (X[3 * id + k] - mean[k]) * scale;
+  }
+  if (translation) for (int k = 0; k < 3; ++k) translation[k] = mean[k];
+  if (scale_out) *scale_out = scale;
+}
+
+}  // namespace
+
+extern "C" void psfm_ba_default_refine_options(psfm_ba_refine_options* r) {
+  r->max_refinements = 5;                 // ba_global_max_refinements, controllers/global_mapper.h:68
+  r->max_refinement_change = 0.0005;      // ba_global_max_refinement_change, :69
+  r->filter_max_reproj_error = 4.0;       // sfm/global_mapper.h:53
+  r->filter_min_tri_angle = 1.5;          // :56
+  r->normalize_extent = 10.0;             // Reconstruction::Normalize defaults, base/reconstruction.h
+  r->normalize_p0 = 0.1;
+  r->normalize_p1 = 0.9;
+}
+
+extern "C" int psfm_ba_filter_negative_depth(psfm_ba_solver* S, int64_t* num_filtered) {
+  if (!S) return PSFM_ERR_INVALID;
+  try {
+    const long long n = filter_negative_depth_impl(S);
+    if (num_filtered) *num_filtered = n;
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+extern "C" int psfm_ba_filter_points(psfm_ba_solver* S, double max_reproj_error, double min_tri_angle_deg, int64_t* num_filtered) {
+  if (!S || !(max_reproj_error >= 0.0) || !(min_tri_angle_deg >= 0.0)) return PSFM_ERR_INVALID;
+  try {
+    const long long n = filter_points_impl(S, max_reproj_error, min_tri_angle_deg);
+    if (num_filtered) *num_filtered = n;
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+extern "C" int psfm_ba_normalize(psfm_ba_solver* S, double extent, double p0, double p1, double* translation, double* scale) {
+  if (!S || !(extent > 0.0) || !(p0 >= 0.0 && p0 <= p1 && p1 <= 1.0)) return PSFM_ERR_INVALID;   // CHECKs :375-380
+  try {
+    normalize_impl(S, extent, p0, p1, translation, scale);
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+extern "C" int psfm_ba_num_observations(psfm_ba_solver* S, int64_t* num_alive) {
+  if (!S) return PSFM_ERR_INVALID;
+  try {
+    ensure_structure(S);
+    if (num_alive) *num_alive = total_observations_all_ranks(S);
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+extern "C" int psfm_ba_get_observation_mask(psfm_ba_solver* S, uint8_t* alive) {
+  if (!S || !alive) return PSFM_ERR_INVALID;
+  try {
+    if (S->M0) PSFM_CUDA(cudaMemcpyAsync(alive, S->d_alive.p, (size_t)S->M0, cudaMemcpyDeviceToHost, S->stream));
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+extern "C" int psfm_ba_get_point_errors(psfm_ba_solver* S, double* error) {
+  if (!S || !error) return PSFM_ERR_INVALID;
+  try {
+    if (S->d_pt_error.n != (size_t)S->P_total) {
+      for (int k = 0; k < S->P_total; ++k) error[k] = nan("");
+      return PSFM_OK;
+    }
+    if (S->P_total) PSFM_CUDA(cudaMemcpyAsync(error, S->d_pt_error.p, sizeof(double) * (size_t)S->P_total, cudaMemcpyDeviceToHost, S->stream));
+    PSFM_CUDA(cudaStreamSynchronize(S->stream));
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
+}
+
+// IterativeGlobalRefinement (controllers/global_mapper.cc:245-271) on the resident problem, minus the
+// IncrementalTriangulator calls (CompleteAndMergeTracks / Retriangulate: out of scope, 0 changes):
+// <= max_refinements rounds of { AdjustGlobalBundle = negative-depth filter, BA, Normalize ;
+// FilterAllPoints3D }, until the changed fraction drops below max_refinement_change.
+extern "C" int psfm_ba_iterative_refinement(psfm_ba_solver* S, const psfm_ba_options* opts, const psfm_ba_refine_options* ropts,
+                                            psfm_ba_refine_report* report) {
+  if (!S) return PSFM_ERR_INVALID;
+  psfm_ba_refine_options r;
+  if (ropts) r = *ropts; else psfm_ba_default_refine_options(&r);
+  psfm_ba_options o;
+  if (opts) o = *opts; else psfm_ba_global_options(&o);
+  if (r.max_refinements <= 0 || r.max_refinements > PSFM_BA_MAX_REFINEMENTS || r.max_refinement_change < 0.0) {   // CHECK_OPTION :84-85
+    set_error("psfm_ba_iterative_refinement: bad refinement options");
+    return PSFM_ERR_INVALID;
+  }
+  if (S->F < 10) {   // kMinNumRegImagesForFastBA, controllers/global_mapper.cc:226-235
+    o.function_tolerance /= 10; o.gradient_tolerance /= 10; o.parameter_tolerance /= 10;
+    o.max_num_iterations *= 2; o.max_linear_solver_iterations = 200;
+  }
+  psfm_ba_refine_report rep;
+  memset(&rep, 0, sizeof(rep));
+  const double t0 = now_s();
+  try {
+    for (int i = 0; i < r.max_refinements; ++i) {
+      ensure_structure(S);
+      const long long num_obs = total_observations_all_ranks(S);
+      rep.num_observations[i] = num_obs;
+      rep.num_negative_depth[i] = filter_negative_depth_impl(S);
+      psfm_ba_summary sum;
+      const int rc = run_impl(S, &o, &sum);
+      if (rc < 0) return rc;
+      rep.ba_iterations[i] = sum.num_iterations;
+      rep.ba_final_cost[i] = sum.final_cost;
+      rep.ba_termination[i] = sum.termination;
+      if (rc == PSFM_OK) normalize_impl(S, r.normalize_extent, r.normalize_p0, r.normalize_p1, nullptr, nullptr);
+      const long long changed = filter_points_impl(S, r.filter_max_reproj_error, r.filter_min_tri_angle);
+      rep.num_changed[i] = changed;
+      rep.changed[i] = num_obs > 0 ? (double)changed / (double)num_obs : 0.0;
+      rep.num_rounds = i + 1;
+      if (rep.changed[i] < r.max_refinement_change) break;
+    }
+    ensure_structure(S);
+    rep.final_num_observations = total_observations_all_ranks(S);
+    rep.total_time_in_seconds = now_s() - t0;
+    if (report) *report = rep;
+    return PSFM_OK;
+  } catch (const CudaFail& f) { return f.code; }
 }
 
 extern "C" int psfm_ba_band_solve(const double* A, const double* b, int32_t nb, int32_t bw, double* x) {
@@ -1655,10 +1962,11 @@ extern "C" int psfm_ba_linear_step(psfm_ba_solver* S, const psfm_ba_options* opt
   if (!S) return PSFM_ERR_INVALID;
   try {
     RunCfg c;
+    ensure_structure(S);
     sync_observed_flags(S);
     int rc = resolve_cfg(S, opts, c);
     if (rc != PSFM_OK) return rc;
-      S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
+    S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
     upload_state(S);
     set_masks_and_unit_scale(S, c);
     linearize_and_measure(S, c, radius, false, true);
