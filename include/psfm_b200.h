@@ -162,8 +162,9 @@ typedef struct {
   int32_t max_num_consecutive_invalid_steps; /* 10 (bundle_adjustment.h:89) */
   int32_t linear_solver;             /* psfm_ba_linear_solver */
   double eta;                        /* 0.1 Ceres default (forcing sequence) */
-  double exact_r_tolerance;          /* 1e-13: |r|/|b| target of the EXACT_SCHUR mode */
-  int32_t exact_max_iterations;      /* 0 -> 20 * reduced dimension */
+  double exact_r_tolerance;          /* 1e-10: |r|/|b| target when EXACT_SCHUR has to fall back to PCG (reduced system too
+                                        large to factor, principal point refined) */
+  int32_t exact_max_iterations;      /* 0 -> min(20000, max(1000, 5 * reduced dimension)) */
   double initial_trust_region_radius;/* 1e4 */
   double max_trust_region_radius;    /* 1e16 */
   double min_trust_region_radius;    /* 1e-32 */

@@ -334,6 +334,17 @@ def flatten(reconstruction, config):
         obs_point.append(np.array([pt_index[int(p)] for p in im.point3D_ids[sel]], np.int32))
         obs_xy.append(np.asarray(im.xys, np.float64)[sel])
     cat = (lambda l, shape, dt: np.concatenate(l) if l else np.zeros(shape, dt))
+    # ParameterizePoints (bundle_adjustment.cc:546-552) holds constant every point whose track is longer
+    # than its residuals in the problem (it is also seen by images outside the config).  The flattened
+    # problem has no constant points (the global BA adds every registered image): refuse instead of
+    # silently moving points the reference would hold fixed.
+    if obs_point:
+        in_cfg = np.bincount(np.concatenate(obs_point), minlength=len(pt_ids))
+        for k, pid in enumerate(pt_ids):
+            p3 = reconstruction.points3D[pid]
+            if p3.image_ids is not None and in_cfg[k] and len(p3.image_ids) > in_cfg[k]:
+                raise _lib.PsfmError(f"point {pid} is observed by images outside the BundleAdjustmentConfig: constant points "
+                                     "(bundle_adjustment.cc:546-552) are not supported by the flattened problem")
     F = len(image_ids)
     pose_constant = np.array([config.HasConstantPose(i) for i in image_ids], np.uint8)
     tmask = np.zeros(F, np.uint8)

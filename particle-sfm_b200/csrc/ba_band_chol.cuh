@@ -33,7 +33,14 @@ namespace ba {
 
 constexpr int BC_RING = 8;        // ring of upcoming rows (streamed 4 pivots ahead)
 constexpr int BC_MAXW = 152;      // window limit: (W/4 + 1)(W/4 + 2)/2 workers + W + 4 helper lanes <= 1024 threads
-constexpr int BC_CSM = BC_MAXW + 8;   // FIXED shared-memory row stride of colbuf / ring: addresses become immediates
+constexpr int BC_CSM = 184;       // FIXED shared-memory row stride of colbuf / ring (addresses become immediates):
+                                  // bc_idx(BC_MAXW + 7) < 184
+// Window position p lives at double index p + 2 (p / 16): 16 bytes of padding after every 128.
+// A warp's lanes read 32 consecutive bytes each (their block of 4 positions) with two LDS.128; at a
+// plain 32-byte stride the lanes q and q + 4 of a quarter warp hit the same banks (2-way conflict:
+// measured, the workers were bound by shared-memory wavefronts), with the padding they do not.
+__host__ __device__ __forceinline__ constexpr int bc_idx(int p) { return p + ((p >> 4) << 1); }
+
 constexpr int BC_MAXSLOT = 7;     // 1 + ceil(bw / 32) register slots of the back substitution
 
 struct BandAsmArgs2 {
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
   // column 0
   if (worker && Q == 0) {
 #pragma unroll
-    for (int i = 0; i < BS; ++i) colbuf[BS * P + i] = v[i][0];
+    for (int i = 0; i < BS; ++i) colbuf[bc_idx(BS * P) + i] = v[i][0];
   }
   const long long tk0 = a.prof ? clock64() : 0;
   const int nsteps = ((nb + UN - 1) / UN) * UN;
@@ -201,14 +208,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     for (int i = 0; i < 4; ++i) { rg[i] = live ? __ldg(src) : 0.0; src += RS; }
     int kk = e;                                            // (e - pj) mod W for band entries
     const bool no_out = (a.flags & 1) != 0, no_ring = (a.flags & 16) != 0;
+    const int ce = bc_idx(e);                              // where position e of the pivot column lives
+    // entry (j + kk, kk) of Lr: one element back per pivot, W (LS + 1) forward when kk wraps
+    double* lp = a.Lr + (size_t)e * LS + e;
+    double* la = a.La + (size_t)(live && !band ? e - W : 0) * nb;
     long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
     for (int j0 = 0; j0 < nsteps; j0 += UN) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int j = j0 + u;
         if (!no_ring) {
-          if (live) ring[u * BC_CSM + pos] = rg[u & 3];      // row j + W -> slot u
-          rg[u & 3] = live ? __ldg(src) : 0.0;               // row j + W + 4
+          if (live) ring[u * BC_CSM + bc_idx(pos)] = rg[u & 3];   // row j + W -> slot u
+          rg[u & 3] = live ? __ldg(src) : 0.0;                    // row j + W + 4
         }
         src += RS;
         if (band && ++pos == W) pos = 0;
@@ -220,23 +231,26 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
           p_wait += t - tlast + (dd == 1.25e-300 ? 1 : 0); tlast = t;
         }
         if (j < nb && !no_out) {
-          const double val = colbuf[(u & 1) * BC_CSM + e];
+          const double val = colbuf[(u & 1) * BC_CSM + ce];
           if (band) {
-            if (kk <= bw && j + kk < nb) a.Lr[(size_t)(j + kk) * LS + kk] = val;
+            if (kk <= bw && j + kk < nb) *lp = val;
             if (kk == 0) a.dinv[j] = val;                  // the pivot itself
           } else if (live) {
-            a.La[(size_t)(e - W) * nb + j] = val;
+            la[j] = val;
           }
         }
-        if (band && --kk < 0) kk = W - 1;
+        if (band) {
+          if (--kk < 0) { kk = W - 1; lp += (size_t)W * (LS + 1); }
+          lp -= 1;
+        }
       }
     }
     if (a.prof && tid == ldr0) { a.prof[4] = p_own; a.prof[5] = p_wait; }
   } else {
     // ---- workers (and idle threads of the last worker warp: barriers only)
-    const double* sP = colbuf + BS * P;
-    const double* sQ = colbuf + BS * Q;
-    const double* sD = colbuf;                             // + pj
+    const double* sP = colbuf + bc_idx(BS * P);
+    const double* sQ = colbuf + bc_idx(BS * Q);
+    int pj0 = 0, pjp = 0;                                  // pivot position of step u = 0 of the body, and its padded index
     int Pj = 0;
     long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
     for (int j0 = 0; j0 < nsteps; j0 += UN) {
@@ -246,34 +260,39 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
         const int par = (u & 1) * BC_CSM, parn = ((u + 1) & 1) * BC_CSM, slot = u * BC_CSM;
         if (a.prof) { const long long t = clock64(); p_own += t - tlast; tlast = t; }
         bc_bar();
-        const double d = sD[par + u];
+        const double d = colbuf[par + pjp + u];            // 8 consecutive positions never straddle a padding gap
         bad |= !(d > 0.0 && d <= 1.7976931348623157e308);
         if (a.prof) { const long long t = clock64(); p_wait += t - tlast + (bad ? 0 : 0); tlast = t; }
         if (worker && !(a.flags & 8)) {
           const double invd = (a.flags & 2) ? 1.0 - 1e-3 * d : bc_rcp(d);
-          double cp[BS], tq[BS], np[BS], nq[BS];
+          double cp[BS], tq[BS];
 #pragma unroll
           for (int i = 0; i < BS; i += 2) {
             const double2 x = *reinterpret_cast<const double2*>(sP + par + i);
             const double2 y = *reinterpret_cast<const double2*>(sQ + par + i);
-            const double2 z = *reinterpret_cast<const double2*>(sP + 2 * BC_CSM + slot + i);
-            const double2 w = *reinterpret_cast<const double2*>(sQ + 2 * BC_CSM + slot + i);
             cp[i] = x.x; cp[i + 1] = x.y;
             tq[i] = y.x * invd; tq[i + 1] = y.y * invd;
-            np[i] = z.x; np[i + 1] = z.y;
-            nq[i] = w.x; nq[i + 1] = w.y;
           }
-          const bool ownQ = Q == Pj, ownP = P == Pj;
-          // rank-1 update; the slots of position pj are free afterwards: they take row j + W
+          // rank-1 update
 #pragma unroll
           for (int i = 0; i < BS; ++i)
 #pragma unroll
-            for (int k = 0; k < BS; ++k) {
-              double x = fma(-cp[i], tq[k], v[i][k]);
-              if (k == ij) x = ownQ ? np[i] : x;
-              if (i == ij) x = ownP ? nq[k] : x;
-              v[i][k] = x;
+            for (int k = 0; k < BS; ++k) v[i][k] = fma(-cp[i], tq[k], v[i][k]);
+          // the slots of position pj are free: they take row j + W (only their ~W/4 owners touch the ring)
+          if (Q == Pj) {
+#pragma unroll
+            for (int i = 0; i < BS; i += 2) {
+              const double2 z = *reinterpret_cast<const double2*>(sP + 2 * BC_CSM + slot + i);
+              v[i][ij] = z.x; v[i + 1][ij] = z.y;
             }
+          }
+          if (P == Pj) {
+#pragma unroll
+            for (int k = 0; k < BS; k += 2) {
+              const double2 w = *reinterpret_cast<const double2*>(sQ + 2 * BC_CSM + slot + k);
+              v[ij][k] = w.x; v[ij][k + 1] = w.y;
+            }
+          }
           // publish column j + 1
           const int ijn = (ij + 1) % BS;
           int Pjn = Pj;
@@ -282,18 +301,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
           if (a.flags & 4) {
           } else if (Q == Pjn) {
 #pragma unroll
-            for (int i = 0; i < BS; i += 2) *reinterpret_cast<double2*>(cbn + BS * P + i) = make_double2(v[i][ijn], v[i + 1][ijn]);
+            for (int i = 0; i < BS; i += 2) *reinterpret_cast<double2*>(cbn + bc_idx(BS * P) + i) = make_double2(v[i][ijn], v[i + 1][ijn]);
           } else if (P == Pjn) {
 #pragma unroll
-            for (int k = 0; k < BS; k += 2) *reinterpret_cast<double2*>(cbn + BS * Q + k) = make_double2(v[ijn][k], v[ijn][k + 1]);
+            for (int k = 0; k < BS; k += 2) *reinterpret_cast<double2*>(cbn + bc_idx(BS * Q) + k) = make_double2(v[ijn][k], v[ijn][k + 1]);
           }
           if (ij == BS - 1) Pj = Pjn;
         } else if (ij == BS - 1) {
           if (++Pj == Wb) Pj = 0;
         }
       }
-      sD += UN;
-      if (sD == colbuf + W) sD = colbuf;
+      pj0 += UN;
+      if (pj0 == W) pj0 = 0;
+      pjp = bc_idx(pj0);
     }
     if (a.prof && tid == 0) { a.prof[6] = p_own; a.prof[7] = p_wait; }
   }

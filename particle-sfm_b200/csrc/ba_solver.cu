@@ -335,12 +335,21 @@ int build_structure(psfm_ba_solver* S) {
   int P = 0, maxL = 0;
   while (P < Pt && h_cs[P] > 0) ++P;           // observed points come first
   for (int j = 0; j < P; ++j) maxL = std::max(maxL, h_cs[j]);
+  if (dist::world_size() > 1) {   // every rank takes the same code paths: the longest track of ANY shard decides
+    DBuf<double> mx; mx.alloc(1, st);
+    k_fill<<<1, 32, 0, st>>>(mx.p, (double)maxL, 1); PSFM_LAUNCH_CHECK();
+    dist::allreduce_max(mx.p, 1, st);
+    double h = 0.0;
+    PSFM_CUDA(cudaMemcpyAsync(&h, mx.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    maxL = (int)(h + 0.5);
+  }
   S->P = P; S->maxL = maxL;
   S->pt_orig.assign(h_order.begin(), h_order.begin() + P);
   // A track lives in one tile and a tile's per-image staging grows with the images it spans: beyond
   // 512 observations the shared memory of an SM (227 KB) no longer holds a tile.
   if (maxL > 512) { set_error("a track with more than 512 observations is not supported"); return PSFM_ERR_UNSUPPORTED; }
-  S->tile = maxL <= 256 ? 256 : 512;
+  S->tile = (maxL <= 256 && !getenv("PSFM_TILE512")) ? 256 : 512;
   // tiles: whole points, <= tile observations (greedy, host: P iterations)
   const int TILE = S->tile;
   std::vector<int> pt_ptr(P + 1, 0), tile_start, tile_pt;
@@ -916,10 +925,35 @@ void ensure_pairs(psfm_ba_solver* S) {
     }
     S->bw = 6 * h_span + 5;
   }
-  if (S->npairs >= (1ll << 31)) { set_error("too many observation pairs for the explicit Schur complement"); throw CudaFail{PSFM_ERR_UNSUPPORTED}; }
-  if (M == 0) {   // nothing to contribute: zero accumulators that still take part in the all-reduces
-    S->span = (S->bw - 5) / 6;
-    S->fused = true; S->ntasks = 0;
+  {
+    // an error on one rank is an error on all of them (nobody is left waiting in an all-reduce)
+    double too_many = S->npairs >= (1ll << 31) ? 1.0 : 0.0;
+    if (dist::world_size() > 1) {
+      DBuf<double> fl; fl.alloc(1, st);
+      k_fill<<<1, 32, 0, st>>>(fl.p, too_many, 1); PSFM_LAUNCH_CHECK();
+      dist::allreduce_max(fl.p, 1, st);
+      PSFM_CUDA(cudaMemcpyAsync(&too_many, fl.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      PSFM_CUDA(cudaStreamSynchronize(st));
+    }
+    if (too_many > 0.5) { set_error("too many observation pairs for the explicit Schur complement"); throw CudaFail{PSFM_ERR_UNSUPPORTED}; }
+  }
+  S->span = (S->bw - 5) / 6;
+  {
+    const size_t smem256 = TileSmem<256>::bytes(NVX2, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(NVX2, 15, S->cap_ns, S->cap_np);
+    const size_t smem = S->tile == 256 ? smem256 : smem512;
+    S->fused = smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
+  }
+  if (dist::world_size() > 1) {   // fused and unfused paths all-reduce different buffers: one decision for all ranks
+    DBuf<double> fl; fl.alloc(1, st);
+    k_fill<<<1, 32, 0, st>>>(fl.p, S->fused ? 0.0 : 1.0, 1); PSFM_LAUNCH_CHECK();
+    dist::allreduce_max(fl.p, 1, st);
+    double h = 0.0;
+    PSFM_CUDA(cudaMemcpyAsync(&h, fl.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    S->fused = h < 0.5;
+  }
+  if (M == 0 && S->fused) {   // nothing to contribute: zero accumulators that still take part in the all-reduces
+    S->ntasks = 0;
     S->band_n = (size_t)F * (S->span + 1) * 36; S->band_nrep = 1;
     S->d_xband.alloc((size_t)F * NVX2 + S->band_n, st);
     S->d_bandrep.alloc(S->band_n, st); S->d_bandrep.zero(st);
@@ -938,12 +972,6 @@ void ensure_pairs(psfm_ba_solver* S) {
     cub::DeviceScan::ExclusiveSum(nullptr, need, cnt.p, ptr32.p, M + 1, st);
     DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
     cub::DeviceScan::ExclusiveSum(tmp.p, need, cnt.p, ptr32.p, M + 1, st);
-  }
-  S->span = (S->bw - 5) / 6;
-  {
-    const size_t smem256 = TileSmem<256>::bytes(NVX2, 15, S->cap_ns, S->cap_np), smem512 = TileSmem<512>::bytes(NVX2, 15, S->cap_ns, S->cap_np);
-    const size_t smem = S->tile == 256 ? smem256 : smem512;
-    S->fused = smem <= 227 * 1024 && !getenv("PSFM_SCHUR_UNFUSED");
   }
   if (S->fused) {
     // ---- tile-local tasks for k_schur_tile

@@ -500,6 +500,7 @@ struct Workspace {
   DBuf<psfm_traj_summary> summary;
   size_t cap_n = 0, cap_flow = 0, cap_chunks = 0;
   int grid_limit = 0;
+  int grid_limit_dev = -1;      // the device grid_limit was computed for (psfm_set_device may change it)
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   void ensure(size_t n, size_t nchunks) {
@@ -535,14 +536,16 @@ static int launch_solve(Workspace& ws, const double* d_uv12, const double* d_ref
   if (opts) a.o = *opts; else psfm_traj_default_options(&a.o);
   a.x[0] = ws.x0.p; a.x[1] = ws.x1.p; a.r = ws.r.p; a.jac = ws.jac.p; a.sc = ws.sc.p; a.dg = ws.dg.p;
   a.gt = ws.gt.p; a.gn = ws.gn.p; a.part = ws.part.p; a.out = d_out; a.summary = ws.summary.p;
-  if (ws.grid_limit == 0) {
-    int dev = 0, sms = 0, per_sm = 0, coop = 0;
-    PSFM_CUDA(cudaGetDevice(&dev));
+  int cur_dev = 0;
+  PSFM_CUDA(cudaGetDevice(&cur_dev));
+  if (ws.grid_limit == 0 || ws.grid_limit_dev != cur_dev) {
+    int dev = cur_dev, sms = 0, per_sm = 0, coop = 0;
     PSFM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) { set_error("device does not support cooperative launch"); return PSFM_ERR_UNSUPPORTED; }
     PSFM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PSFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traj_solve, CH, 0));
     ws.grid_limit = std::max(1, sms * per_sm);
+    ws.grid_limit_dev = dev;
   }
   const int grid = std::min(a.nchunks, ws.grid_limit);
   void* kargs[] = {(void*)&a};
