@@ -36,7 +36,8 @@ def _solve(A, b, nb, bw):
 
 # (nb, bw): tiny window, window wider than the matrix, nb not a multiple of 4, the bench shape
 # (6 * 200 images, span 11/12), the 1024-thread instantiation, the widest supported window
-CASES = [(30, 9), (18, 17), (18, 40), (90, 59), (1200, 71), (1200, 77), (600, 127), (3000, 71), (700, 151), (100, 31), (1203, 95)]
+CASES = [(30, 9), (18, 17), (18, 40), (90, 59), (1200, 71), (1200, 77), (600, 127), (3000, 71), (700, 150), (100, 31), (1203, 95),
+         (64, 6), (41, 14), (500, 38)]
 
 
 @pytest.mark.parametrize("nb,bw", CASES)
