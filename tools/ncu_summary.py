@@ -70,6 +70,9 @@ def launch(path, out):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
+    micro = {k: v for k, v in agg.items() if "k_fp64_" in k}      # bench.py's fp64 roof microbenchmark: not part of a step
+    for k in micro:
+        del agg[k]
     tot = sum(a[1] for a in agg.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary of `{path}`\n\n`ncu --metrics gpu__time_duration.sum --clock-control none`; "
@@ -78,6 +81,10 @@ def launch(path, out):
                 f"| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {n} | {t:.1f} | {t / n:.2f} | {100 * t / tot:.1f}% |\n")
+        if micro:
+            f.write("\nNot part of a step (excluded from the shares): " +
+                    ", ".join(f"`{k}` x{n} = {t:.0f} us" for k, (n, t) in micro.items()) +
+                    " — `psfm_measure_dfma`, the fp64 roof microbenchmark `bench.py` runs once per process.\n")
 
 
 if __name__ == "__main__":
