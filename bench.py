@@ -19,8 +19,9 @@ rotations + focal length refined).  `--config N` runs BASELINE.json's configs[N-
 The line also carries the HP1 number (trajectory optimiser, pts/s) under "traj_opt".
 
 `--impl reference` times the CPU arm — the oracle's restatement of the reference's algorithm
-(Ceres LM + SPARSE_SCHUR: block-sparse Schur complement, band Cholesky; OpenMP over all host
-threads, min(ncpu, 64) as sfm/main_sfm.py:144) — on the SAME workload, full size; the sample
+(Ceres LM + SPARSE_SCHUR: block-sparse Schur complement, band Cholesky; OpenMP, the best thread
+count of {8,16,32,64} <= min(ncpu, 64) — the reference's cap, sfm/main_sfm.py:144 — found by a
+short calibration, see cpu_threads()) — on the SAME workload, full size; the sample
 is only shrunk (and said so) when a full-size solve would not fit the driver's time budget.
 """
 import argparse
@@ -143,26 +144,58 @@ def workload_text(w, M):
             f"trajectories x L={w['track_len']} obs/track{extra}, M={M} observations, seed {w['seed']}")
 
 
-def cpu_solve_once(w, num_threads=0):
+_CPU_THREADS = None
+
+
+def cpu_threads(w=None):
+    """Threads of the CPU arm.  The reference takes min(cpu_count, 64) (ctx_init, sfm/main_sfm.py:144); on a
+    two-socket host the memory-bound sweeps stop scaling well before that (measured on the GPU box, 2 x 32
+    cores: 16 threads 3.2 M obs/s, 64 threads 1.9, profiles/r02_cpu_threads.md), so the arm is given the
+    BEST count of {8, 16, 32, 64} <= cpu_count, found with a short calibration solve on 1/10 of the
+    workload — the CPU arm must not lose to its own thread count."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None or w is None:
+        return _CPU_THREADS or 0
+    import oracle
+    from particlesfm_b200 import synthetic as syn, _abi
+    cap = min(oracle.num_threads(), 64)
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= cap} | {min(cap, 8)})
+    if len(cands) > 1:
+        ws = dict(w); ws["num_points"] = max(2000, w["num_points"] // 10)
+        prob, _ = syn.make_ba_problem(**ws)
+        o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
+        o.linear_solver = _abi.SOLVER_AUTO
+        o.max_num_iterations = 3
+        best = None
+        for c in cands:
+            oracle.ba_solve(prob.copy(), o, num_threads=c)
+            t0 = time.perf_counter()
+            oracle.ba_solve(prob.copy(), o, num_threads=c)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, c)
+        _CPU_THREADS = best[1]
+    else:
+        _CPU_THREADS = cands[0]
+    return _CPU_THREADS
+
+
+def cpu_solve_once(w):
     """One solve of the CPU arm on workload w; returns (seconds, summary, problem size M, threads)."""
     import oracle
     from particlesfm_b200 import synthetic as syn, _abi
+    nt = cpu_threads(w)
     prob, _ = syn.make_ba_problem(**w)
     o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
     o.linear_solver = _abi.SOLVER_AUTO
     t0 = time.perf_counter()
-    s = oracle.ba_solve(prob, o, num_threads=num_threads)
-    return time.perf_counter() - t0, s, prob.num_observations, cpu_threads()
-
-
-def cpu_threads():
-    import oracle
-    return min(oracle.num_threads(), 64)      # ctx_init: min(cpu_count, 64), sfm/main_sfm.py:144
+    s = oracle.ba_solve(prob, o, num_threads=nt)
+    return time.perf_counter() - t0, s, prob.num_observations, nt
 
 
 def run_reference(args, rank, cfg):
     """CPU arm: the oracle's restatement of the reference's path (LM + SPARSE_SCHUR for
-    50 < F <= 1000, bundle_adjustment.cc:276-286) on all host threads, same workload."""
+    50 < F <= 1000, bundle_adjustment.cc:276-286) on the host's best thread count (cpu_threads()), same workload."""
     if rank != 0:
         return
     import oracle
@@ -171,12 +204,13 @@ def run_reference(args, rank, cfg):
     if args.points:
         w["num_points"] = args.points
     full_points = w["num_points"]
+    nt = cpu_threads(w)
     prob, _ = syn.make_ba_problem(**w)
     o = oracle.ba_global_options(refine_rotation=True, refine_focal_length=True)
     o.linear_solver = _abi.SOLVER_AUTO
     # first warm-up solve at full size decides whether the whole run fits the budget
     t0 = time.perf_counter()
-    oracle.ba_solve(prob.copy(), o)
+    oracle.ba_solve(prob.copy(), o, num_threads=nt)
     t_full = time.perf_counter() - t0
     total_solves = args.warmup + args.steps
     shrunk = False
@@ -191,14 +225,14 @@ def run_reference(args, rank, cfg):
     for k in range(warm_rest + args.steps):
         p = prob.copy()
         t0 = time.perf_counter()
-        s = oracle.ba_solve(p, o)
+        s = oracle.ba_solve(p, o, num_threads=nt)
         dt = time.perf_counter() - t0
         if k >= warm_rest:
             times.append(dt)
             iters += s.num_iterations
     total = sum(times)
     val = M * len(times) / total
-    cores = cpu_threads()
+    cores = nt
     sample = ("the full workload" if not shrunk else
               f"P={w['num_points']} of {full_points} points (a full-size solve takes {t_full:.1f} s on this host: "
               f"{total_solves} of them exceed the {REFERENCE_BUDGET_S:.0f} s budget)")
@@ -440,7 +474,7 @@ def main():
         "obs_iterations_per_sec": M_total * sum(s.num_iterations for s in summaries) / t_total,
         "device_ms_per_step": sum(s.device_ms for s in summaries) / len(summaries),
         "final_cost": s_last.final_cost, "initial_cost": s_last.initial_cost, "termination": s_last.termination,
-        "ate_vs_truth": ate,
+        "ate_vs_truth": ate, "pair_entries": int(s_last.num_pair_entries), "pair_units": int(s_last.num_pair_tasks),
         "e2e": {"value": e2e_val, "unit": "observations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None},
         "gpu_launches": int(launches),

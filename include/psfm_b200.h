@@ -123,6 +123,29 @@ int psfm_traj_optimize_device(const double* d_uv12, const double* d_ref1,
                               psfm_traj_summary* summary, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Tracker stage around HP1: the float32 sampling,        */
+/* survival test and re-seeding of point_trajectory/trajectory.py:25-62,117-194  */
+/* and the forward/backward flow check of point_trajectory/utils.py:58-105, bit   */
+/* for bit as torch's CPU grid_sample / scipy's distance transform produce them   */
+/* (csrc/tracker.cu).  Host buffers in, host buffers out; maps are [H][W][C].      */
+/* ------------------------------------------------------------------------- */
+/* grid_sample(map, xy) of trajectory.py:25-37: bilinear, zeros padding, align_corners;
+   channels 1 or 2; out [n][channels] float32 */
+int psfm_grid_sample(const float* map, int32_t h, int32_t w, int32_t channels, const double* xy, int32_t n, float* out);
+/* flow_check for one frame pair: err [H][W] (may be NULL), occ [H][W] = err > thres or out of bounds */
+int psfm_flow_check(const float* flow_f, const float* flow_b, int32_t h, int32_t w, float thres, float* err, uint8_t* occ);
+/* step_forward + the re-seeding mask of extend_all for all live particles:
+   next_xy = cur_xy + flow(cur_xy); flags[i] = inside the image and occlusion(cur_xy) <= 0.1;
+   reseed_mask [ceil(H/r)][ceil(W/r)] (may be NULL) = distance_transform_edt(1 - occupied) > r on the
+   r-strided grid, occupied = the pixels (int(y), int(x)) of the survivors' next positions (needs >= 1 survivor) */
+int psfm_tracker_step(const float* flow, const uint8_t* occ, int32_t h, int32_t w, const double* cur_xy, int32_t n,
+                      int32_t sample_ratio, double* next_xy, uint8_t* flags, uint8_t* reseed_mask);
+/* optimize_buffer's inputs (trajectory.py:171-183): ref1 = x0 + flow01(x0), ref2 = x0 + flow02(x0),
+   scale = (1 - occ02(x0)) * (|flow02(x0)| < upper_flow) */
+int psfm_tracker_buffer_inputs(const float* flow01, const float* flow02, const uint8_t* occ02, int32_t h, int32_t w,
+                               const double* x0, int32_t n, double upper_flow, double* ref1, double* ref2, double* scale);
+
+/* ------------------------------------------------------------------------- */
 /* HP2 — global bundle adjustment                                             */
 /* ------------------------------------------------------------------------- */
 

@@ -19,7 +19,8 @@ EXPORTS = [
     "psfm_ba_set_state", "psfm_ba_run", "psfm_ba_get_state", "psfm_ba_destroy", "psfm_ba_evaluate",
     "psfm_ba_linear_step", "psfm_ba_band_solve", "psfm_measure_dfma", "psfm_ba_default_refine_options",
     "psfm_ba_filter_negative_depth", "psfm_ba_filter_points", "psfm_ba_normalize", "psfm_ba_num_observations",
-    "psfm_ba_get_observation_mask", "psfm_ba_get_point_errors", "psfm_ba_iterative_refinement", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
+    "psfm_ba_get_observation_mask", "psfm_ba_get_point_errors", "psfm_ba_iterative_refinement",
+    "psfm_grid_sample", "psfm_flow_check", "psfm_tracker_step", "psfm_tracker_buffer_inputs", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
     "psfm_dist_rank", "psfm_dist_finalize",
 ]
 
@@ -61,6 +62,11 @@ def lib():
     L.psfm_ba_evaluate.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), dp, dp, dp, dp]
     L.psfm_ba_linear_step.argtypes = [C.c_void_p, C.POINTER(_abi.BAOptions), C.c_double, dp, dp, ip]
     L.psfm_measure_dfma.argtypes = [dp, dp]
+    u8p = C.POINTER(C.c_uint8)
+    L.psfm_grid_sample.argtypes = [fp, C.c_int32, C.c_int32, C.c_int32, dp, C.c_int32, fp]
+    L.psfm_flow_check.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_float, fp, u8p]
+    L.psfm_tracker_step.argtypes = [fp, u8p, C.c_int32, C.c_int32, dp, C.c_int32, C.c_int32, dp, u8p, u8p]
+    L.psfm_tracker_buffer_inputs.argtypes = [fp, fp, u8p, C.c_int32, C.c_int32, dp, C.c_int32, C.c_double, dp, dp, dp]
     i64p = C.POINTER(C.c_int64)
     L.psfm_ba_default_refine_options.argtypes = [C.POINTER(_abi.BARefineOptions)]
     L.psfm_ba_default_refine_options.restype = None

@@ -28,6 +28,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", CXX
 UNITS = [
     ("common.cu", []),
     ("microbench.cu", []),
+    ("tracker.cu", []),
     ("dist.cu", []),
     ("ba_solver.cu", []),
     ("traj_solver.cu", ["-fmad=false"]),

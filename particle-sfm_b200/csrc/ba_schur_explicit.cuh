@@ -247,6 +247,7 @@ struct StArgs {
   double* Sband;                 // [nrep][F * (span + 1) * 36]
   size_t band_stride;
   int nrep_mask;
+  int dbg;      // PSFM_SCHUR_FLAGS (measurement only): 1 = no band REDs, 2 = no pair loop
 };
 
 // One tile of the fused Schur kernel; shared memory holds the staged inputs (see linearize_tile).
@@ -342,7 +343,7 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
   // entry 24 shared-memory loads (the kernel is bound by shared-memory wavefronts, not by the
   // fp64 pipe) and ~110 flops.  Two lanes per task (even | odd entries), the full 6x6 block in
   // registers, one shuffle per element to combine, 18 REDs per lane.  Uniform trip count.
-  const int nq = 2 * nt;
+  const int nq = (a.dbg & 2) ? 0 : 2 * nt;
   for (int q0 = 0; q0 < nq; q0 += TILE) {
     const int q = q0 + tid;
     const bool valid = q < nq;
@@ -407,7 +408,7 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
 #pragma unroll
     for (int k = 0; k < 36; ++k)
       if (ROT || (k / 6 >= 3 && k % 6 >= 3)) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-    if (valid) {
+    if (valid && !(a.dbg & 1)) {
       double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * par;
 #pragma unroll
       for (int k = 0; k < 18; ++k) {
@@ -500,39 +501,51 @@ __global__ void k_pair_fill_tile(const int* pt_ptr, const int* obs_pt, const int
   }
 }
 
-// tasks of a tile are processed longest first (lanes of a warp then run similar trip counts and
-// the short tasks fill the last pass): sort key (tile, ~count), payload = task index
-__global__ void k_task_sortkeys(const unsigned long long* ukeys, const int* ucount, int ntasks, int fbits,
-                                unsigned long long* key2, int* idx) {
+// A run of equal keys (one image pair of one tile) is cut into UNITS of at most `chunk` entries, all
+// of (nearly) the same length; a unit is what two lanes of k_schur_tile accumulate in registers.
+// Without the cut the longest run of a tile (every point of the tile sees both images) sets the trip
+// count of its warp while the other warps wait at the end-of-tile barrier.
+__global__ void k_unit_count(const int* ucount, int nruns, int chunk, int* nunits) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntasks) return;
-  key2[t] = ((ukeys[t] >> (2 * fbits)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)ucount[t]);
-  idx[t] = t;
+  if (t > nruns) return;
+  nunits[t] = t < nruns ? (ucount[t] + chunk - 1) / chunk : 0;
 }
-__global__ void k_task_gather(const int* order, const int* slot_in, const int* beg_in, int ntasks, int* slot_out, int2* rng_out) {
+// units of a tile are processed longest first (lanes of a warp then run similar trip counts and the
+// short units fill the last pass): sort key (tile, ~count), payload = (slot, entry range)
+__global__ void k_unit_fill(const unsigned long long* ukeys, const int* ucount, const int* beg, const int* ubeg, int nruns,
+                            int fbits, int span, unsigned long long* key2, int* idx, int* slot, int2* rng) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nruns) return;
+  const unsigned long long k = ukeys[t], mask = (1ull << fbits) - 1;
+  const int b = (int)(k & mask), a = (int)((k >> fbits) & mask);
+  const unsigned long long tile = k >> (2 * fbits);
+  const int n = ubeg[t + 1] - ubeg[t], cnt = ucount[t], base = cnt / n, rem = cnt % n;
+  int e = beg[t];
+  for (int c = 0; c < n; ++c) {
+    const int len = base + (c < rem), u = ubeg[t] + c;
+    key2[u] = (tile << 32) | (unsigned long long)(0xffffffffu - (unsigned)len);
+    idx[u] = u;
+    slot[u] = a * (span + 1) + (b - a);
+    rng[u] = make_int2(e, e + len);
+    e += len;
+  }
+}
+__global__ void k_task_gather(const int* order, const int* slot_in, const int2* rng_in, int ntasks, int* slot_out, int2* rng_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntasks) return;
   const int o = order[t];
   slot_out[t] = slot_in[o];
-  rng_out[t] = make_int2(beg_in[o], beg_in[o + 1]);
+  rng_out[t] = rng_in[o];
 }
 
-// task t (one run of equal keys) -> band-block slot; tile -> first task (lower bound)
-__global__ void k_task_slots(const unsigned long long* ukeys, int ntasks, int fbits, int span, int* slot) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntasks) return;
-  const unsigned long long k = ukeys[t], mask = (1ull << fbits) - 1;
-  const int b = (int)(k & mask), a = (int)((k >> fbits) & mask);
-  slot[t] = a * (span + 1) + (b - a);
-}
-
-__global__ void k_tile_tasks(const unsigned long long* ukeys, int ntasks, int fbits, int T, int* tile_task) {
+// tile -> first unit (lower bound over the sorted (tile, ~count) keys)
+__global__ void k_tile_tasks(const unsigned long long* key2_sorted, int ntasks, int T, int* tile_task) {
   const int tile = blockIdx.x * blockDim.x + threadIdx.x;
   if (tile > T) return;
-  int lo = 0, hi = ntasks;      // first task whose tile >= this tile
+  int lo = 0, hi = ntasks;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if ((int)(ukeys[mid] >> (2 * fbits)) < tile) lo = mid + 1; else hi = mid;
+    if ((int)(key2_sorted[mid] >> 32) < tile) lo = mid + 1; else hi = mid;
   }
   tile_task[tile] = lo;
 }

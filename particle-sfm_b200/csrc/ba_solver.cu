@@ -998,31 +998,43 @@ void ensure_pairs(psfm_ba_solver* S) {
       DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
       cub::DeviceRunLengthEncode::Encode(tmp.p, need, k64_out.p, uk64.p, ucount.p, nruns.p, (int)NPr, st);
     }
+    int nr = 0;
+    PSFM_CUDA(cudaMemcpyAsync(&nr, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaStreamSynchronize(st));
+    // runs -> units of <= chunk entries (k_unit_count / k_unit_fill)
+    int chunk = 8;
+    if (const char* e = getenv("PSFM_TASK_CHUNK")) chunk = std::max(1, atoi(e));
+    DBuf<int> beg0, nun, ubeg;
+    beg0.alloc((size_t)nr + 1, st); nun.alloc((size_t)nr + 1, st); ubeg.alloc((size_t)nr + 1, st);
+    PSFM_CUDA(cudaMemsetAsync(ucount.p + nr, 0, sizeof(int), st));
+    k_unit_count<<<grid_for((size_t)nr + 1), 256, 0, st>>>(ucount.p, nr, chunk, nun.p); PSFM_LAUNCH_CHECK();
+    {
+      size_t need = 0, need2 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, ucount.p, beg0.p, nr + 1, st);
+      cub::DeviceScan::ExclusiveSum(nullptr, need2, nun.p, ubeg.p, nr + 1, st);
+      DBuf<unsigned char> tmp; tmp.alloc(std::max(need, need2) + 256, st);
+      cub::DeviceScan::ExclusiveSum(tmp.p, need, ucount.p, beg0.p, nr + 1, st);
+      cub::DeviceScan::ExclusiveSum(tmp.p, need2, nun.p, ubeg.p, nr + 1, st);
+    }
     int nt = 0;
-    PSFM_CUDA(cudaMemcpyAsync(&nt, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSFM_CUDA(cudaMemcpyAsync(&nt, ubeg.p + nr, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSFM_CUDA(cudaStreamSynchronize(st));
     S->ntasks = nt;
     S->d_task_slot.alloc(nt, st); S->d_task_rng.alloc(nt, st); S->d_tile_task.alloc((size_t)T + 1, st);
-    DBuf<int> slot0, beg0, idx0, order;
+    DBuf<int> slot0, idx0, order;
+    DBuf<int2> rng0;
     DBuf<unsigned long long> key2, key2_out;
-    slot0.alloc(nt, st); beg0.alloc((size_t)nt + 1, st); idx0.alloc(nt, st); order.alloc(nt, st); key2.alloc(nt, st); key2_out.alloc(nt, st);
-    PSFM_CUDA(cudaMemsetAsync(ucount.p + nt, 0, sizeof(int), st));
-    {
-      size_t need = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, need, ucount.p, beg0.p, nt + 1, st);
-      DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
-      cub::DeviceScan::ExclusiveSum(tmp.p, need, ucount.p, beg0.p, nt + 1, st);
-    }
+    slot0.alloc(nt, st); rng0.alloc(nt, st); idx0.alloc(nt, st); order.alloc(nt, st); key2.alloc(nt, st); key2_out.alloc(nt, st);
     if (nt) {
-      k_task_slots<<<grid_for(nt), 256, 0, st>>>(uk64.p, nt, fb, S->span, slot0.p); PSFM_LAUNCH_CHECK();
-      k_task_sortkeys<<<grid_for(nt), 256, 0, st>>>(uk64.p, ucount.p, nt, fb, key2.p, idx0.p); PSFM_LAUNCH_CHECK();
+      k_unit_fill<<<grid_for(nr), 256, 0, st>>>(uk64.p, ucount.p, beg0.p, ubeg.p, nr, fb, S->span, key2.p, idx0.p, slot0.p, rng0.p);
+      PSFM_LAUNCH_CHECK();
       size_t need = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, need, key2.p, key2_out.p, idx0.p, order.p, nt, 0, 32 + tb, st);
       DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
       cub::DeviceRadixSort::SortPairs(tmp.p, need, key2.p, key2_out.p, idx0.p, order.p, nt, 0, 32 + tb, st);
-      k_task_gather<<<grid_for(nt), 256, 0, st>>>(order.p, slot0.p, beg0.p, nt, S->d_task_slot.p, S->d_task_rng.p); PSFM_LAUNCH_CHECK();
+      k_task_gather<<<grid_for(nt), 256, 0, st>>>(order.p, slot0.p, rng0.p, nt, S->d_task_slot.p, S->d_task_rng.p); PSFM_LAUNCH_CHECK();
     }
-    k_tile_tasks<<<grid_for((size_t)T + 1), 256, 0, st>>>(uk64.p, nt, fb, T, S->d_tile_task.p);
+    k_tile_tasks<<<grid_for((size_t)T + 1), 256, 0, st>>>(key2_out.p, nt, T, S->d_tile_task.p);
     PSFM_LAUNCH_CHECK();
     S->band_n = (size_t)F * (S->span + 1) * 36;
     int nrep = 8;   // the pair-task REDs are spread over many band blocks: few replicas suffice (fold cost grows with them)
@@ -1188,6 +1200,7 @@ void do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
   w.K = S->d_K[S->cur].p; w.acc_cam = S->d_xcamrep.p; w.rep_stride = nx; w.intr = c.intr;
   w.entries = S->d_tentries.p; w.task_slot = S->d_task_slot.p; w.task_rng = S->d_task_rng.p; w.tile_task = S->d_tile_task.p;
   w.Sband = S->d_bandrep.p; w.band_stride = S->band_n; w.nrep_mask = S->band_nrep - 1;
+  { static const int dbg = getenv("PSFM_SCHUR_FLAGS") ? atoi(getenv("PSFM_SCHUR_FLAGS")) : 0; w.dbg = dbg; }
   auto mark = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, bool begin) {
     cudaEvent_t e = S->events.get();
     PSFM_CUDA(cudaEventRecord(e, st));

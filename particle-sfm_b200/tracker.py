@@ -24,7 +24,81 @@ Semantics that decide the INTEGER TRACK CONNECTIVITY are kept bit-for-bit:
     ratio-strided grid,
   * trajectory ids are the positions in the reference's `full_trajs` list (retire order).
 """
+import ctypes as _C
+
 import numpy as np
+
+
+# ----------------------------------------------------------------------------- device ops (csrc/tracker.cu)
+
+def _f32p(a):
+    return a.ctypes.data_as(_C.POINTER(_C.c_float))
+
+
+def _u8p(a):
+    return a.ctypes.data_as(_C.POINTER(_C.c_uint8))
+
+
+def grid_sample_device(map_hwc, xy):
+    """grid_sample (trajectory.py:25-37) on the GPU, bit for bit what torch's CPU kernel returns.
+    map_hwc: [H, W, C] float32 (C = 1 or 2) or [H, W]; xy [N, 2] float64 -> [N, C] float32."""
+    from . import _lib
+    m = np.ascontiguousarray(map_hwc, np.float32)
+    if m.ndim == 2:
+        m = m[:, :, None]
+    h, w, c = m.shape
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    out = np.empty((xy.shape[0], c), np.float32)
+    _lib.check(_lib.lib().psfm_grid_sample(_f32p(m), h, w, c, _lib.dptr(xy), xy.shape[0], _f32p(out)), "psfm_grid_sample")
+    return out
+
+
+def flow_check_device(flows, flows_b, thres):
+    """flow_check (point_trajectory/utils.py:58-105) on the GPU -> (error_maps, occ_maps)."""
+    from . import _lib
+    error_maps, occ_maps = [], []
+    for f, f_b in zip(flows, flows_b):
+        f = np.ascontiguousarray(f, np.float32)
+        f_b = np.ascontiguousarray(f_b, np.float32)
+        h, w = f.shape[:2]
+        err = np.empty((h, w), np.float32)
+        occ = np.empty((h, w), np.uint8)
+        _lib.check(_lib.lib().psfm_flow_check(_f32p(f), _f32p(f_b), h, w, float(thres), _f32p(err), _u8p(occ)), "psfm_flow_check")
+        error_maps.append(err)
+        occ_maps.append(occ.astype(bool))
+    return error_maps, occ_maps
+
+
+def tracker_step_device(flow, occ, cur_xy, sample_ratio):
+    """step_forward + the re-seeding mask of extend_all -> (next_xy, flags, reseed_mask or None)."""
+    from . import _lib
+    flow = np.ascontiguousarray(flow, np.float32)
+    occ8 = np.ascontiguousarray(occ, np.uint8)
+    h, w = flow.shape[:2]
+    cur = np.ascontiguousarray(cur_xy, np.float64).reshape(-1, 2)
+    n = cur.shape[0]
+    nxt = np.empty((n, 2), np.float64)
+    flags = np.zeros(n, np.uint8)
+    gh, gw = -(-h // sample_ratio), -(-w // sample_ratio)
+    mask = np.zeros((gh, gw), np.uint8)
+    _lib.check(_lib.lib().psfm_tracker_step(_f32p(flow), _u8p(occ8), h, w, _lib.dptr(cur), n, sample_ratio, _lib.dptr(nxt),
+                                            _u8p(flags), _u8p(mask)), "psfm_tracker_step")
+    return nxt, flags, (mask.astype(bool) if flags.any() else None)
+
+
+def buffer_inputs_device(flow01, flow02, occ02, x0, upper_flow=20.0):
+    """optimize_buffer's ref1, ref2, scale (trajectory.py:171-183) on the GPU."""
+    from . import _lib
+    f1 = np.ascontiguousarray(flow01, np.float32)
+    f2 = np.ascontiguousarray(flow02, np.float32)
+    o2 = np.ascontiguousarray(occ02, np.uint8)
+    h, w = f1.shape[:2]
+    x0 = np.ascontiguousarray(x0, np.float64).reshape(-1, 2)
+    n = x0.shape[0]
+    ref1, ref2, scale = np.empty((n, 2)), np.empty((n, 2)), np.empty((n, 1))
+    _lib.check(_lib.lib().psfm_tracker_buffer_inputs(_f32p(f1), _f32p(f2), _u8p(o2), h, w, _lib.dptr(x0), n, float(upper_flow),
+                                                     _lib.dptr(ref1), _lib.dptr(ref2), _lib.dptr(scale)), "psfm_tracker_buffer_inputs")
+    return ref1, ref2, scale
 
 
 def grid_sample(data, xy):
@@ -70,9 +144,10 @@ def flow_check(flows, flows_b, thres):
 class BatchedTrajectorySet:
     """SoA replacement of IncrementalTrajectorySet (buffer_size = 3)."""
 
-    def __init__(self, total_length, img_h, img_w, sample_ratio, optimize_fn):
+    def __init__(self, total_length, img_h, img_w, sample_ratio, optimize_fn, device=False):
         self.total_length, self.h, self.w, self.ratio = total_length, img_h, img_w, sample_ratio
         self.optimize_fn = optimize_fn
+        self.device = device            # True: sampling / survival / re-seeding on the GPU (csrc/tracker.cu)
         x, y = np.arange(0, img_w), np.arange(0, img_h)
         xx, yy = np.meshgrid(x, y)
         self.all_candidates = np.stack([xx, yy], -1)[::sample_ratio, ::sample_ratio, :]
@@ -115,13 +190,11 @@ class BatchedTrajectorySet:
         return self.xy_at[self.cur_time][self.act_i0]
 
     # -- extend_all (trajectory.py:129-152)
-    def extend_all(self, next_xys, next_time, flags):
+    def extend_all(self, next_xys, next_time, flags, reseed_mask=None):
         assert len(next_xys) == self.act_id.shape[0] == len(flags)
         keep = np.asarray(flags) != 0
         self.retired.append(self.act_id[~keep])
-        occupied = np.zeros((self.h, self.w, 1))
         nx = next_xys[keep]
-        occupied[nx[:, 1].astype(np.int64), nx[:, 0].astype(np.int64)] = 1      # int() truncation
         n = int(keep.sum())
         self.ids_at[next_time], self.xy_at[next_time] = self.act_id[keep], nx.astype(np.float64)
         self.act_id = self.act_id[keep]
@@ -130,9 +203,14 @@ class BatchedTrajectorySet:
         self.act_im1 = self.act_i0[keep]
         self.act_i0 = np.arange(n, dtype=np.int64)
         self.cur_time = next_time
-        import scipy.ndimage
-        dist = scipy.ndimage.distance_transform_edt(1.0 - occupied)
-        sample_map = (dist > self.ratio)[::self.ratio, ::self.ratio, 0]
+        if reseed_mask is not None:          # computed on the device with the step (exact: squared integer distances)
+            sample_map = reseed_mask
+        else:
+            import scipy.ndimage
+            occupied = np.zeros((self.h, self.w, 1))
+            occupied[nx[:, 1].astype(np.int64), nx[:, 0].astype(np.int64)] = 1      # int() truncation
+            dist = scipy.ndimage.distance_transform_edt(1.0 - occupied)
+            sample_map = (dist > self.ratio)[::self.ratio, ::self.ratio, 0]
         self.sample_candidates = np.copy(self.all_candidates[sample_map])
 
     def clear_active(self):
@@ -151,12 +229,15 @@ class BatchedTrajectorySet:
         if sel.shape[0] == 0:
             raise ValueError("need at least one array to stack")     # np.stack([]) in the reference
         h, w = flow01_map.shape[0], flow01_map.shape[1]
-        flow01 = grid_sample(torch.from_numpy(flow01_map).permute(2, 0, 1).float(), x0)
-        flow02 = grid_sample(torch.from_numpy(flow02_map).permute(2, 0, 1).float(), x0)
-        occ02 = grid_sample(torch.from_numpy(occ02_map).unsqueeze(0).float(), x0)
-        scale = (1.0 - occ02) * (np.linalg.norm(flow02, axis=-1, keepdims=True) < upper_flow)
-        ref1 = x0 + flow01
-        ref2 = x0 + flow02
+        if self.device:
+            ref1, ref2, scale = buffer_inputs_device(flow01_map, flow02_map, occ02_map, x0, upper_flow)
+        else:
+            flow01 = grid_sample(torch.from_numpy(flow01_map).permute(2, 0, 1).float(), x0)
+            flow02 = grid_sample(torch.from_numpy(flow02_map).permute(2, 0, 1).float(), x0)
+            occ02 = grid_sample(torch.from_numpy(occ02_map).unsqueeze(0).float(), x0)
+            scale = (1.0 - occ02) * (np.linalg.norm(flow02, axis=-1, keepdims=True) < upper_flow)
+            ref1 = x0 + flow01
+            ref2 = x0 + flow02
         uv12 = np.concatenate([x1, x2], axis=1)
         new = self.optimize_fn(uv12, ref1, ref2, scale, flow12_map, uv12.shape[0], w, h)
         new = np.asarray(new, np.float64).reshape(-1, 2, 2)
@@ -190,19 +271,27 @@ def _default_optimize():
     return traj.optimize_location
 
 
-def track_optimize(flows, flows_f2, occ_maps, occ_maps_s2, sample_ratio, optimize_fn=None, traj_min_len=0):
+def track_optimize(flows, flows_f2, occ_maps, occ_maps_s2, sample_ratio, optimize_fn=None, traj_min_len=0, device=False):
     """Sequentially track and optimise point trajectories (track_optimize.py:24-54).
     Returns {traj_id: {"frame_ids", "locations", "labels"}} with the reference's ids
     (= positions in its `full_trajs` list); `traj_min_len` applies the filter of
-    main_connect_point_trajectories.py:57-60."""
+    main_connect_point_trajectories.py:57-60.  device=True: the float32 sampling, the survival test and
+    the re-seeding run on the GPU (same bits, csrc/tracker.cu) instead of torch-CPU / scipy."""
     import torch
     optimize_fn = optimize_fn or _default_optimize()
     n_flows = len(flows)
     h, w = flows[0].shape[:2]
-    trajs = BatchedTrajectorySet(n_flows + 1, h, w, sample_ratio, optimize_fn)
+    trajs = BatchedTrajectorySet(n_flows + 1, h, w, sample_ratio, optimize_fn, device=device)
     for frame_id in range(n_flows):
         trajs.new_traj_all(frame_id, trajs.sample_candidates)
         cur_xys = trajs.get_cur_pos()
+        if device:
+            next_xys, flags, mask = tracker_step_device(flows[frame_id], occ_maps[frame_id], cur_xys, sample_ratio)
+            trajs.extend_all(next_xys, frame_id + 1, flags, mask)
+            if frame_id + 1 >= 2:
+                trajs.optimize_buffer(flows[frame_id - 1], flows[frame_id], flows_f2[frame_id - 1],
+                                      occ_maps_s2[frame_id - 1], frame_id + 1)
+            continue
         flow_sample = grid_sample(torch.from_numpy(flows[frame_id]).permute(2, 0, 1).float(), cur_xys)
         # step_forward (trajectory.py:45-62)
         occ = grid_sample(torch.from_numpy(occ_maps[frame_id]).unsqueeze(0).float(), cur_xys) > 0.1
@@ -218,10 +307,11 @@ def track_optimize(flows, flows_f2, occ_maps, occ_maps_s2, sample_ratio, optimiz
 
 
 def main_connect_point_trajectories(flows_f, flows_b, flows_f2, flows_b2, sample_ratio=2, flow_check_thres=1.0,
-                                    traj_min_len=3, optimize_fn=None):
+                                    traj_min_len=3, optimize_fn=None, device=False):
     """In-memory equivalent of main_connect_point_trajectories.py:27-62 with
     skip_path_consistency=False: returns the dict a `particlesfm.TrajectorySet` is built
     from (and np.save'd as track.npy)."""
-    _, occ = flow_check(flows_f, flows_b, flow_check_thres)
-    _, occ2 = flow_check(flows_f2, flows_b2, flow_check_thres)
-    return track_optimize(flows_f, flows_f2, occ, occ2, sample_ratio, optimize_fn, traj_min_len)
+    fc = flow_check_device if device else flow_check
+    _, occ = fc(flows_f, flows_b, flow_check_thres)
+    _, occ2 = fc(flows_f2, flows_b2, flow_check_thres)
+    return track_optimize(flows_f, flows_f2, occ, occ2, sample_ratio, optimize_fn, traj_min_len, device=device)
