@@ -24,7 +24,17 @@
 //                    corner one more thread.  Then L' x = y by warp 0 in axpy form (per pivot:
 //                    one multiply, one shuffle, one fma on the chain), the rows of L staged
 //                    chunk-wise into shared memory by the other warps.
-// tools/emu_band_chol.py is a thread-level numpy emulation of exactly this index logic.
+//                    TWO-SIDED form (gridDim.x = 2, matrices of >= 4 windows): the chain of nb dependent
+//                    pivots is cut in two.  CTA 0 factors the leading k0 pivots of A top-down, CTA 1
+//                    the trailing n1 pivots bottom-up (the same code on the index-reversed matrix);
+//                    the W rows in between (W > bw, so no top pivot touches a bottom pivot: the two
+//                    eliminations commute) collect both Schur updates — CTA 1 hands its update of
+//                    that W x W block, of the arrow and of the corner over through global memory,
+//                    CTA 0 adds it to its register window and finishes the last W pivots and the
+//                    corner.  The back substitution mirrors it: CTA 0 solves the middle rows first
+//                    and releases them, then both CTAs walk outwards.  Same arithmetic per pivot as
+//                    the one-sided form, different (but fixed) elimination order.
+// tools/emu_band_chol.py is a thread-level numpy emulation of the one-sided window logic.
 #pragma once
 #include "ba_schur_explicit.cuh"
 
@@ -43,6 +53,17 @@ __host__ __device__ __forceinline__ constexpr int bc_idx(int p) { return p + ((p
 
 constexpr int BC_MAXSLOT = 7;     // 1 + ceil(bw / 32) register slots of the back substitution
 
+// Split of the pivot chain (band_chol_plan): one-sided (two = 0) or two-sided.
+struct BandPlan {
+  int nb, bw, W, RS;
+  int two;                  // 1: two CTAs
+  int nbp;                  // nb rounded up to 8 (identity padding rows)
+  int k0, n1;               // pivots factored top-down before the hand-over | bottom-up; k0 + W + n1 = nbp
+  int nbs[2];               // rows of the matrix each side sees: k0 + W | n1 + W   (one-sided: nb | 0)
+  int npiv[2];              // pivots each side factors:           k0 + W | n1       (one-sided: nb | 0)
+  int rows[2];              // rows of Ab each side may touch (band_chol_rows)
+};
+
 struct BandAsmArgs2 {
   const double* Sband;      // [F][span + 1][36] all-reduced pair-block sums
   const double* lin_cam;    // [F][NVL]  F'F rot (6) | t (6) | ...
@@ -54,9 +75,12 @@ struct BandAsmArgs2 {
   const double* Dc2;        // [NS]
   const double* rhs;        // [NS]
   const unsigned char* active;
-  int F, span, nb, bw, W, RS, nrows;
-  double* Ab;               // [nrows][RS]: Ab[r][k] = A[r][r - k] (k <= bw), Ab[r][W + a] = A[nb + a][r], a < 3; Ab[r][W + 3] = rhs[r]
-  double* C4;               // [4][4] arrow corner: intrinsics block (3 x 3) | rhs entries in row / column 3
+  int F, span;
+  BandPlan pl;
+  double* Ab;               // side 0 [rows[0]][RS]: Ab[r][k] = A[r][r - k] (k <= bw), Ab[r][W + a] = A[nb + a][r], a < 3; Ab[r][W + 3] = rhs[r]
+  double* Ab1;              // side 1 [rows[1]][RS]: the same of the index-reversed matrix, middle block and middle arrow zero
+  double* C4;               // [2][4][4] arrow corner: intrinsics block (3 x 3) | rhs entries in row / column 3; side 1: zero
+  int* fail;                // cleared here, set by k_band_chol
 };
 
 // packed index of element (r, c) of a symmetric 3 x 3 stored as 00 01 02 11 12 22
@@ -65,62 +89,116 @@ __device__ __forceinline__ int sym3(int r, int c) {
   return lo * (5 - lo) / 2 + hi;
 }
 
-__global__ void k_band_assemble(const BandAsmArgs2 a) {
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < 16) {   // corner (camera 0: intrinsics are only ever free for a single shared camera)
-    const int r = (int)t / 4, c = (int)t % 4;
-    const size_t sk = 6 * (size_t)a.F;
-    double v = 0.0;
-    if (r < 3 && c < 3) {
-      v = a.scale_c[sk + r] * a.scale_c[sk + c] * (a.lin_intr[sym3(r, c)] + a.prep_intr[sym3(r, c)]);
-      if (r == c) { if (a.active[sk + r]) v += a.Dc2[sk + r]; else v = 1.0; }
-    } else if (r == 3 && c < 3) v = a.rhs[sk + c];
-    else if (c == 3 && r < 3) v = a.rhs[sk + r];
-    a.C4[t] = v;
-  }
-  if (t >= (size_t)a.nrows * a.RS) return;
-  const int r = (int)(t / a.RS), e = (int)(t % a.RS);
+// scaled reduced-system element A[r][r - e] of the band part (0 <= e <= bw, r - e >= 0), identity below nb
+__device__ __forceinline__ double band_entry(const BandAsmArgs2& a, int r, int e) {
+  if (r >= a.pl.nb) return e == 0 ? 1.0 : 0.0;
+  const int c = r - e;
   double v = 0.0;
-  if (r >= a.nb) {
-    v = (e == 0) ? 1.0 : 0.0;                       // identity padding below the band part
-  } else if (e < a.W) {
-    const int c = r - e;
-    if (e <= a.bw && c >= 0) {
-      const int ia = r / 6, rr = r % 6, ib = c / 6, cc = c % 6, d = ia - ib;
-      const double ss = a.scale_c[r] * a.scale_c[c];
-      if (d <= a.span)     // lower element (r, c): mirror of the stored upper block (ib, ib + d)
-        v = -ss * a.Sband[((size_t)ib * (a.span + 1) + d) * 36 + (d ? 6 * cc + rr : 6 * rr + cc)];
-      if (d == 0) {
-        const double* A = a.lin_cam + (size_t)ia * NVL;
-        if (rr < 3) v += ss * A[sym3(rr, cc)];                                   // cc <= rr < 3
-        else if (cc >= 3) v += ss * A[6 + sym3(rr - 3, cc - 3)];
-        else v += ss * a.xcam[(size_t)ia * a.xstride + 3 * cc + (rr - 3)];     // (Jr' Jt)[cc][rr - 3]
-        if (e == 0) { if (a.active[r]) v += a.Dc2[r]; else v = 1.0; }
-      }
-    }
-  } else {
-    const int aa = e - a.W;
-    if (aa == 3) v = a.rhs[r];
-    else if (aa == 0) {
-      const double* X = a.xcam + (size_t)(r / 6) * a.xstride;
-      v = a.scale_c[r] * a.scale_c[6 * (size_t)a.F] * (X[9 + r % 6] + X[15 + r % 6]);
-    }
+  const int ia = r / 6, rr = r % 6, ib = c / 6, cc = c % 6, d = ia - ib;
+  const double ss = a.scale_c[r] * a.scale_c[c];
+  if (d <= a.span)     // lower element (r, c): mirror of the stored upper block (ib, ib + d)
+    v = -ss * a.Sband[((size_t)ib * (a.span + 1) + d) * 36 + (d ? 6 * cc + rr : 6 * rr + cc)];
+  if (d == 0) {
+    const double* A = a.lin_cam + (size_t)ia * NVL;
+    if (rr < 3) v += ss * A[sym3(rr, cc)];                                   // cc <= rr < 3
+    else if (cc >= 3) v += ss * A[6 + sym3(rr - 3, cc - 3)];
+    else v += ss * a.xcam[(size_t)ia * a.xstride + 3 * cc + (rr - 3)];     // (Jr' Jt)[cc][rr - 3]
+    if (e == 0) { if (a.active[r]) v += a.Dc2[r]; else v = 1.0; }
   }
-  a.Ab[t] = v;
+  return v;
+}
+// arrow entry aa of column r: A[nb + aa][r] (aa < 3) | rhs[r] (aa = 3); zero below nb
+__device__ __forceinline__ double arrow_entry(const BandAsmArgs2& a, int r, int aa) {
+  if (r >= a.pl.nb) return 0.0;
+  if (aa == 3) return a.rhs[r];
+  if (aa == 0) {
+    const double* X = a.xcam + (size_t)(r / 6) * a.xstride;
+    return a.scale_c[r] * a.scale_c[6 * (size_t)a.F] * (X[9 + r % 6] + X[15 + r % 6]);
+  }
+  return 0.0;
 }
 
-struct BandCholArgs {
+__global__ void k_band_assemble(const BandAsmArgs2 a) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const BandPlan& pl = a.pl;
+  if (t == 0) *a.fail = 0;
+  if (t < 32) {   // corner (camera 0: intrinsics are only ever free for a single shared camera); side 1 starts from zero
+    const int r = ((int)t & 15) / 4, c = (int)t % 4;
+    const size_t sk = 6 * (size_t)a.F;
+    double v = 0.0;
+    if (t < 16) {
+      if (r < 3 && c < 3) {
+        v = a.scale_c[sk + r] * a.scale_c[sk + c] * (a.lin_intr[sym3(r, c)] + a.prep_intr[sym3(r, c)]);
+        if (r == c) { if (a.active[sk + r]) v += a.Dc2[sk + r]; else v = 1.0; }
+      } else if (r == 3 && c < 3) v = a.rhs[sk + c];
+      else if (c == 3 && r < 3) v = a.rhs[sk + r];
+    }
+    a.C4[t] = v;
+  }
+  const int RS = pl.RS, W = pl.W;
+  const size_t n0 = (size_t)pl.rows[0] * RS, n1 = (size_t)pl.rows[1] * RS;
+  if (t < n0) {
+    const int r = (int)(t / RS), e = (int)(t % RS);
+    double v = 0.0;
+    if (r >= min(pl.nb, pl.nbs[0])) {
+      v = (e == 0) ? 1.0 : 0.0;                       // identity padding below the part this side factors
+    } else if (e < W) {
+      if (e <= pl.bw && r - e >= 0) v = band_entry(a, r, e);
+    } else {
+      v = arrow_entry(a, r, e - W);
+    }
+    a.Ab[t] = v;
+  } else if (t < n0 + n1) {
+    // index-reversed matrix B[r'][c'] = A[nbp-1-r'][nbp-1-c']: its lower element (r', r' - e) is the
+    // lower element (R, R - e) of A with R = nbp - 1 - (r' - e).  Rows / columns >= n1 are the middle
+    // block, which side 0 owns: zero here, so that what is left in the window is the pure update.
+    const size_t u = t - n0;
+    const int r = (int)(u / RS), e = (int)(u % RS);
+    double v = 0.0;
+    if (r >= pl.nbs[1]) {
+      v = (e == 0) ? 1.0 : 0.0;
+    } else if (e < W) {
+      const int c = r - e;
+      if (e <= pl.bw && c >= 0 && !(r >= pl.n1 && c >= pl.n1)) v = band_entry(a, pl.nbp - 1 - c, e);
+    } else if (r < pl.n1) {
+      v = arrow_entry(a, pl.nbp - 1 - r, e - W);
+    }
+    a.Ab1[u] = v;
+  }
+}
+
+struct BandSide {
   const double* Ab;
   const double* C4;
-  int nb, bw, W, RS, ns;    // ns: length of x (slots past nb + 3 — other cameras — are zeroed)
+  int nb, npiv;             // rows of this side's matrix | pivots it factors (multiple of 8 in the two-sided form)
   double* Lr;               // [nb][bw + 1]  UNNORMALISED columns: Lr[r][k] = A~[r][r - k] (= L[r][r - k] sqrt(d[r - k]))
   double* La;               // [4][nb]       unnormalised arrow rows (row 3 = rhs)
   double* dinv;             // [nb]          pivots d[j], replaced by 1 / sqrt(d[j]) after the factorisation
-  double* x;                // [ns]
-  int* fail;
-  int flags;                // timing experiments (PSFM_CHOL_FLAGS; results invalid): 1 no output of L, 2 no reciprocal, 4 no publish, 8 barrier + pivot load only, 16 no row streaming
-  long long* prof;          // optional [8]: SM cycles of factorisation | corner + staging | back substitution, pivots
 };
+
+struct BandCholArgs {
+  BandSide s[2];            // blockIdx.x = side
+  int two, nbg, nbp, k0;    // two-sided | rows of the whole matrix | padded to 8 | pivots of side 0 before the hand-over
+  int bw, W, RS, ns;        // ns: length of x (slots past nbg + 3 — other cameras — are zeroed)
+  double* x;                // [ns]
+  int* fail;                // OR of both sides (cleared by k_band_assemble)
+  double* D;                // hand-over of side 1: [W][W] update of the middle block (A orientation) | [4][W] arrow | [16] corner
+  int* sync;                // [2] = epoch once: 0 the hand-over is written, 1 the middle x and the intrinsics are written
+  int epoch;
+  int flags;                // timing experiments (PSFM_CHOL_FLAGS; results invalid): 1 no output of L, 2 no reciprocal, 4 no publish, 8 barrier + pivot load only, 16 no row streaming
+  long long* prof;          // optional [8]: SM cycles of factorisation | corner + staging | back substitution, pivots (side 0)
+};
+
+__device__ __forceinline__ void bc_post(int* flag, int v) {
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bc_wait(const int* flag, int v) {
+  int x;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(x) : "l"(flag) : "memory");
+  } while (x != v);
+}
 
 // bar.sync 0 from role-specific loops: every thread of the CTA executes the same NUMBER of
 // barriers, from different program counters.  Measured on B200: one warp runs dependent scalar
@@ -150,7 +228,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
   __shared__ int s_fail;
   __shared__ double s_xI[4];
   constexpr int UN = 8;                     // pivots per unrolled body: ring slot and colbuf parity are compile-time
-  const int W = a.W, Wb = W / BS, RS = a.RS, nb = a.nb, bw = a.bw, LS = bw + 1;
+  const int side = blockIdx.x;
+  // this side's pointers in registers (indexing the parameter block with blockIdx.x would turn every use into a
+  // dependent constant-bank load inside the pivot loop)
+  BandSide sd;
+  sd.Ab = side ? a.s[1].Ab : a.s[0].Ab; sd.C4 = side ? a.s[1].C4 : a.s[0].C4;
+  sd.nb = side ? a.s[1].nb : a.s[0].nb; sd.npiv = side ? a.s[1].npiv : a.s[0].npiv;
+  sd.Lr = side ? a.s[1].Lr : a.s[0].Lr; sd.La = side ? a.s[1].La : a.s[0].La; sd.dinv = side ? a.s[1].dinv : a.s[0].dinv;
+  const int W = a.W, Wb = W / BS, RS = a.RS, nb = sd.nb, npiv = sd.npiv, bw = a.bw, LS = bw + 1;
+  const int jswitch = (a.two && side == 0) ? a.k0 : -1;
   double* colbuf = bc_smem;                 // [2][BC_CSM]   pivot column by window position (double buffered)
   double* ring = colbuf + 2 * BC_CSM;       // [BC_RING][BC_CSM] upcoming rows, permuted to window positions
   double* stage = ring + BC_RING * BC_CSM;  // [2][32][LSP] coefficients of the back substitution
@@ -177,9 +263,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
       if (worker) {
         if (P < Wb) {
           const int rp = BS * P + i, rq = BS * Q + k, hi = max(rp, rq), lo = min(rp, rq);
-          x = __ldg(a.Ab + (size_t)hi * RS + (hi - lo));
-        } else if (Q < Wb) { if (i < 4) x = __ldg(a.Ab + (size_t)(BS * Q + k) * RS + W + i); }
-        else if (i < 4 && k < 4) x = __ldg(a.C4 + 4 * i + k);
+          x = __ldg(sd.Ab + (size_t)hi * RS + (hi - lo));
+        } else if (Q < Wb) { if (i < 4) x = __ldg(sd.Ab + (size_t)(BS * Q + k) * RS + W + i); }
+        else if (i < 4 && k < 4) x = __ldg(sd.C4 + 4 * i + k);
       }
       v[i][k] = x;
     }
@@ -190,7 +276,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     for (int i = 0; i < BS; ++i) colbuf[bc_idx(BS * P) + i] = v[i][0];
   }
   const long long tk0 = a.prof ? clock64() : 0;
-  const int nsteps = ((nb + UN - 1) / UN) * UN;
+  const int nsteps = ((npiv + UN - 1) / UN) * UN;
+  const int jsplit = jswitch >= 0 ? jswitch : nsteps;      // end of phase 0
   bool bad = false;
 
   if (helper) {
@@ -199,7 +286,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     //      pivot j, position e of the pivot column is entry (e - pj) mod W of column j of L (unnormalised).
     const int e = tid - ldr0;
     const bool band = e < W, live = e < W + 4;
-    const double* src = a.Ab + (size_t)W * RS + e;        // row W
+    const double* src = sd.Ab + (size_t)W * RS + e;       // row W
     int pos = band ? (e == 0 ? 0 : W - e) : e;            // (W - e) mod W: position of entry e of row W
     // rows travel global -> register (4 pivots ahead) -> ring: plain loads, NOT cp.async — a pending
     // LDGSTS is a pending shared-memory write, and bar.sync drains those (measured: ~600 cycles / pivot)
@@ -210,10 +297,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     const bool no_out = (a.flags & 1) != 0, no_ring = (a.flags & 16) != 0;
     const int ce = bc_idx(e);                              // where position e of the pivot column lives
     // entry (j + kk, kk) of Lr: one element back per pivot, W (LS + 1) forward when kk wraps
-    double* lp = a.Lr + (size_t)e * LS + e;
-    double* la = a.La + (size_t)(live && !band ? e - W : 0) * nb;
+    double* lp = sd.Lr + (size_t)e * LS + e;
+    double* la = sd.La + (size_t)(live && !band ? e - W : 0) * nb;
     long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
-    for (int j0 = 0; j0 < nsteps; j0 += UN) {
+    // two phases (before | after the hand-over of the two-sided form) around ONE copy of the pivot loop:
+    // the hand-over code stays out of the loop body (instruction cache), the one-sided form has an empty phase 1
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1 && jswitch >= 0) { bc_bar(); bc_bar(); }    // hand-over of side 1 (workers, below)
+    const int jend = phase == 0 ? jsplit : nsteps;
+#pragma unroll 1
+    for (int j0 = phase == 0 ? 0 : jsplit; j0 < jend; j0 += UN) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int j = j0 + u;
@@ -234,7 +328,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
           const double val = colbuf[(u & 1) * BC_CSM + ce];
           if (band) {
             if (kk <= bw && j + kk < nb) *lp = val;
-            if (kk == 0) a.dinv[j] = val;                  // the pivot itself
+            if (kk == 0) sd.dinv[j] = val;                 // the pivot itself
           } else if (live) {
             la[j] = val;
           }
@@ -245,6 +339,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
         }
       }
     }
+    }
     if (a.prof && tid == ldr0) { a.prof[4] = p_own; a.prof[5] = p_wait; }
   } else {
     // ---- workers (and idle threads of the last worker warp: barriers only)
@@ -253,7 +348,38 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     int pj0 = 0, pjp = 0;                                  // pivot position of step u = 0 of the body, and its padded index
     int Pj = 0;
     long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0;
-    for (int j0 = 0; j0 < nsteps; j0 += UN) {
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 1 && jswitch >= 0) {
+        // two-sided form: the window now holds rows k0 .. k0 + W - 1 with the updates of the pivots above;
+        // add side 1's updates of the same rows (pivots below), then publish column k0 again
+        if (tid == 0) bc_wait(a.sync, a.epoch);
+        bc_bar();
+        if (worker) {
+          const int kw = a.k0 % W;
+          const double* DA = a.D + (size_t)W * W;
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int k = 0; k < BS; ++k) {
+              const int mk = (BS * Q + k - kw + W) % W;      // position -> row of the middle block
+              if (P < Wb) v[i][k] += __ldcg(a.D + (size_t)((BS * P + i - kw + W) % W) * W + mk);
+              else if (Q < Wb) { if (i < 4) v[i][k] += __ldcg(DA + (size_t)i * W + mk); }
+              else if (i < 4 && k < 4) v[i][k] += __ldcg(DA + 4 * (size_t)W + 4 * i + k);
+            }
+          if (Q == Pj) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) colbuf[bc_idx(BS * P) + i] = v[i][0];
+          } else if (P == Pj) {
+#pragma unroll
+            for (int k = 0; k < BS; ++k) colbuf[bc_idx(BS * Q) + k] = v[0][k];
+          }
+        }
+        bc_bar();
+      }
+    const int jend = phase == 0 ? jsplit : nsteps;
+#pragma unroll 1
+    for (int j0 = phase == 0 ? 0 : jsplit; j0 < jend; j0 += UN) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int ij = u % BS;
@@ -315,16 +441,40 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
       if (pj0 == W) pj0 = 0;
       pjp = bc_idx(pj0);
     }
+    }
     if (a.prof && tid == 0) { a.prof[6] = p_own; a.prof[7] = p_wait; }
   }
   __syncthreads();
   const long long tk1 = a.prof ? clock64() : 0;
-  if (a.prof && tid == 0) { a.prof[0] = tk1 - tk0; a.prof[3] = nsteps; }
+  if (a.prof && tid == 0 && side == 0) { a.prof[0] = tk1 - tk0; a.prof[3] = nsteps; }
   if (bad) s_fail = 1;
+  if (a.two && side == 1) {
+    // hand-over: what is left in the window (rows n1 .. n1 + W - 1 of the reversed matrix, zero on input)
+    // is the update of the middle block by this side's pivots; reversed row n1 + m is middle row W - 1 - m
+    if (worker) {
+      const int kw = npiv % W;
+      double* DA = a.D + (size_t)W * W;
+#pragma unroll
+      for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+          const int mk = W - 1 - (BS * Q + k - kw + W) % W;
+          if (P < Wb) {
+            const int mi = W - 1 - (BS * P + i - kw + W) % W;
+            a.D[(size_t)mi * W + mk] = v[i][k];
+            if (P != Q) a.D[(size_t)mk * W + mi] = v[i][k];
+          } else if (Q < Wb) { if (i < 4) DA[(size_t)i * W + mk] = v[i][k]; }
+          else if (i < 4 && k < 4) DA[4 * (size_t)W + 4 * i + k] = v[i][k];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) bc_post(a.sync, a.epoch);
+  }
   // 1 / sqrt(d): normalisation of the stored columns, applied while staging the back substitution
-  for (int j = tid; j < nb; j += blockDim.x) a.dinv[j] = rsqrt(__ldcg(a.dinv + j));
+  for (int j = tid; j < npiv; j += blockDim.x) sd.dinv[j] = rsqrt(__ldcg(sd.dinv + j));
   // ---- arrow corner: 3 x 3 intrinsics block and its right-hand side (thread of block {Wb, Wb})
-  if (tid == NT - 1) {
+  if (side == 0 && tid == NT - 1) {
     bool cbad = false;
     const double m00 = v[0][0], m10 = v[1][0], m20 = v[2][0], m11 = v[1][1], m21 = v[2][1], m22 = v[2][2];
     cbad |= !(m00 > 0.0);
@@ -341,36 +491,59 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     if (cbad || !isfinite(x0 + x1 + x2)) s_fail = 1;
   }
   __syncthreads();
-  if (tid == 0) *a.fail = s_fail;
-  if (s_fail) return;
-  for (int s = nb + tid; s < a.ns; s += blockDim.x) a.x[s] = (s < nb + 3) ? s_xI[s - nb] : 0.0;
+  if (tid == 0 && s_fail) atomicOr(a.fail, 1);
+  if (side == 0) {
+    if (s_fail) {
+      if (a.two && tid == 0) bc_post(a.sync + 1, a.epoch);     // side 1 must not wait for ever
+      return;
+    }
+    for (int s = a.nbg + tid; s < a.ns; s += blockDim.x) a.x[s] = (s < a.nbg + 3) ? s_xI[s - a.nbg] : 0.0;
+  } else {
+    // the middle x and the intrinsics come from side 0
+    if (tid == 0) {
+      bc_wait(a.sync + 1, a.epoch);
+      for (int k = 0; k < 3; ++k) s_xI[k] = __ldcg(a.x + a.nbg + k);
+    }
+    __syncthreads();
+  }
 
   // ---- back substitution L' x = y - La' x_I in axpy form (warp 0; the other warps stage).
   //      Lane l holds the running right-hand side of positions 32 (c - m) + l, m = 0 .. msv-1, of the
   //      current 32-column chunk c.  stage[jj][32 + k] = -L[r][r - k] for 1 <= k <= bw (r = 32 c + jj),
   //      zero elsewhere, so the inner step is one shared load and one fma per slot — no predicates;
-  //      per pivot one multiply, one shuffle and one fma are on the dependent chain.
+  //      per pivot one fma, one shuffle and one fma are on the dependent chain.  Rows >= npiv (side 1:
+  //      the middle rows) are not solved for: their x is known and only propagated.
   const int ms = 1 + (bw + 31) / 32;
   const int msv = ms <= 4 ? 4 : BC_MAXSLOT;
   const int LSP = 32 * (msv + 1);
   const int ctop = (nb + 31) / 32 - 1;
+  const int cpost = (a.two && side == 0) ? a.k0 / 32 : -1;     // after this chunk every middle x is written
   const int CH = 32 * LSP;
+  // one row per warp and pass; all loads of a row (<= 7 x 2 per lane) are issued before the first use — with a
+  // dependent load pair per element the staging, not the substitution chain, set the pace (measured: 7.5 k cycles
+  // per 32-row chunk against 1.3 k for the chain)
   auto stage_chunk = [&](int c, double* buf, int w0, int nw) {
     for (int jj = w0; jj < 32; jj += nw) {
       const int r = 32 * c + jj;
-      for (int q = lane; q < LSP; q += 32) {
-        const int k = q - 32;
-        double val = 0.0;
-        if (k >= 1 && k <= bw && r < nb && r - k >= 0) val = -__ldcg(a.Lr + (size_t)r * LS + k) * __ldcg(a.dinv + r - k);
-        buf[jj * LSP + q] = val;
+      double lv[BC_MAXSLOT], dv[BC_MAXSLOT];
+#pragma unroll
+      for (int t = 0; t < BC_MAXSLOT; ++t) {
+        const int k = lane + 32 * t;                       // element q = 32 (t + 1) + lane of the padded row
+        const bool ok = t < msv && k >= 1 && k <= bw && r < nb && r - k >= 0 && r - k < npiv;
+        lv[t] = ok ? __ldcg(sd.Lr + (size_t)r * LS + k) : 0.0;
+        dv[t] = ok ? __ldcg(sd.dinv + r - k) : 0.0;
       }
+      buf[jj * LSP + lane] = 0.0;
+#pragma unroll
+      for (int t = 0; t < BC_MAXSLOT; ++t)
+        if (t < msv) buf[jj * LSP + 32 * (t + 1) + lane] = -lv[t] * dv[t];
     }
   };
   const double xi0 = s_xI[0], xi1 = s_xI[1], xi2 = s_xI[2];
   auto y0 = [&](int i) -> double {
-    if (i < 0 || i >= nb) return 0.0;
-    return __ldcg(a.dinv + i) * (__ldcg(a.La + 3 * (size_t)nb + i) -
-           (xi0 * __ldcg(a.La + i) + xi1 * __ldcg(a.La + (size_t)nb + i) + xi2 * __ldcg(a.La + 2 * (size_t)nb + i)));
+    if (i < 0 || i >= npiv) return 0.0;
+    return __ldcg(sd.dinv + i) * (__ldcg(sd.La + 3 * (size_t)nb + i) -
+           (xi0 * __ldcg(sd.La + i) + xi1 * __ldcg(sd.La + (size_t)nb + i) + xi2 * __ldcg(sd.La + 2 * (size_t)nb + i)));
   };
   const int wid = tid >> 5, nwarp = blockDim.x >> 5;
   stage_chunk(ctop, stage, wid, nwarp);
@@ -386,35 +559,42 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     } else {
       const double fresh = (c > 0) ? y0(32 * (c - ms) + lane) : 0.0;     // slot ms - 1 of the next chunk
       const int jl = 32 * c + lane;
-      const double dl = (jl < nb) ? __ldcg(a.dinv + jl) : 0.0;
+      const double dl = (jl < npiv) ? __ldcg(sd.dinv + jl) : 0.0;
+      // global index of local row jl: side 0 jl, side 1 nbp - 1 - jl; rows past nbg are identity padding (x = 0)
+      const int gl = side ? a.nbp - 1 - jl : jl;
+      const bool inx = jl < nb && gl >= 0 && gl < a.nbg;
+      const double xk = (jl >= npiv && inx) ? __ldcg(a.x + gl) : 0.0;   // known x (side 1: middle rows)
+      const bool wr = jl < npiv && inx;
+      double* xw = a.x + (inx ? gl : 0);
       const double* rp = buf + 31 * LSP + 32 + (31 - lane);             // &stage[jj][32 + jj - lane], jj = 31
       const int step = LSP + 1;
-      double* xo = a.x + 32 * c;
       if (msv == 4) {
 #pragma unroll 8
         for (int jj = 31; jj >= 0; --jj) {
-          const double xj = __shfl_sync(0xffffffffu, yy[0] * dl, jj);
+          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
 #pragma unroll
           for (int m = 0; m < 4; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
-          if (lane == jj && jl < nb) xo[jj] = xj;
+          if (lane == jj && wr) *xw = xj;
           rp -= step;
         }
       } else {
 #pragma unroll 4
         for (int jj = 31; jj >= 0; --jj) {
-          const double xj = __shfl_sync(0xffffffffu, yy[0] * dl, jj);
+          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
 #pragma unroll
           for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
-          if (lane == jj && jl < nb) xo[jj] = xj;
+          if (lane == jj && wr) *xw = xj;
           rp -= step;
         }
       }
 #pragma unroll
       for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = (m == ms - 1) ? fresh : ((m + 1 < BC_MAXSLOT) ? yy[m + 1] : 0.0);
+      if (c == cpost) __threadfence();
     }
     __syncthreads();
+    if (c == cpost && tid == 0) bc_post(a.sync + 1, a.epoch);
   }
-  if (a.prof && tid == 0) {
+  if (a.prof && tid == 0 && side == 0) {
     const long long tk3 = clock64();
     a.prof[0] = tk1 - tk0; a.prof[1] = tk2 - tk1; a.prof[2] = tk3 - tk2; a.prof[3] = nsteps;
   }
@@ -440,12 +620,69 @@ inline int band_chol_window(int bw) {
 // rows of Ab the kernel may touch (padding rows below the band part are identity rows)
 inline int band_chol_rows(int nb, int W) { return ((nb + 7) & ~7) + W + 8; }
 
-// one launch (4 x 4 register blocks)
+// How the pivot chain is cut.  Two-sided from 4 windows on (below that the hand-over costs more than
+// the shorter chain saves); PSFM_CHOL_ONE_SIDED forces the one-CTA form.
+inline BandPlan band_chol_plan(int nb, int bw) {
+  BandPlan p{};
+  p.nb = nb; p.bw = std::min(bw, nb - 1);
+  p.W = band_chol_window(p.bw); p.RS = p.W + 4;
+  p.nbp = (nb + 7) & ~7;
+  static const bool one = getenv("PSFM_CHOL_ONE_SIDED") != nullptr;
+  p.two = (p.W > 0 && !one && p.nbp >= 4 * p.W) ? 1 : 0;
+  if (p.two) {
+    p.k0 = (((p.nbp - p.W) / 2 + 7) / 8) * 8;
+    p.n1 = p.nbp - p.W - p.k0;
+    p.nbs[0] = p.k0 + p.W; p.npiv[0] = p.k0 + p.W;
+    p.nbs[1] = p.n1 + p.W; p.npiv[1] = p.n1;
+    p.rows[0] = band_chol_rows(p.nbs[0], p.W); p.rows[1] = band_chol_rows(p.nbs[1], p.W);
+  } else {
+    p.nbs[0] = nb; p.npiv[0] = nb; p.rows[0] = p.W ? band_chol_rows(nb, p.W) : 0;
+  }
+  return p;
+}
+
+// device buffers of one plan
+struct BandWork {
+  BandPlan pl{};
+  DBuf<double> Ab, C4, Lr, La, dinv, D;
+  DBuf<int> sync;
+  int epoch = 0;
+  void alloc(const BandPlan& p, cudaStream_t st) {
+    pl = p;
+    const size_t LS = p.bw + 1;
+    Ab.alloc((size_t)(p.rows[0] + p.rows[1]) * p.RS, st);
+    C4.alloc(32, st);
+    Lr.alloc((size_t)(p.nbs[0] + p.nbs[1]) * LS, st); Lr.zero(st);
+    La.alloc(4 * (size_t)(p.nbs[0] + p.nbs[1]), st);
+    dinv.alloc((size_t)p.nbs[0] + p.nbs[1], st);
+    D.alloc((size_t)p.W * p.W + 4 * (size_t)p.W + 16, st);
+    sync.alloc(2, st); sync.zero(st);
+    epoch = 0;
+  }
+  double* ab(int side) { return Ab.p + (side ? (size_t)pl.rows[0] * pl.RS : 0); }
+  BandCholArgs args(double* x, int ns, int* fail) {
+    BandCholArgs c{};
+    const size_t LS = pl.bw + 1;
+    for (int s = 0; s < 2; ++s) {
+      const size_t o = s ? (size_t)pl.nbs[0] : 0;
+      c.s[s].Ab = ab(s); c.s[s].C4 = C4.p + 16 * s; c.s[s].nb = pl.nbs[s]; c.s[s].npiv = pl.npiv[s];
+      c.s[s].Lr = Lr.p + o * LS; c.s[s].La = La.p + 4 * o; c.s[s].dinv = dinv.p + o;
+    }
+    c.two = pl.two; c.nbg = pl.nb; c.nbp = pl.nbp; c.k0 = pl.k0;
+    c.bw = pl.bw; c.W = pl.W; c.RS = pl.RS; c.ns = ns;
+    c.x = x; c.fail = fail; c.D = D.p; c.sync = sync.p; c.epoch = ++epoch;
+    c.prof = nullptr;
+    return c;
+  }
+};
+
+// one launch (4 x 4 register blocks): one CTA, or two for the two-sided form
 inline void band_chol_launch(BandCholArgs c, cudaStream_t st) {
   static const int flags = getenv("PSFM_CHOL_FLAGS") ? atoi(getenv("PSFM_CHOL_FLAGS")) : 0;
   c.flags = flags;
   const int threads = band_chol_threads(c.W, 4);
   const size_t smem = band_chol_smem(c.bw);
+  const int grid = c.two ? 2 : 1;
 #define PSFM_BC_GO(BSV, MT)                                                                                        \
   do {                                                                                                             \
     static size_t attr = 0;                                                                                        \
@@ -453,7 +690,7 @@ inline void band_chol_launch(BandCholArgs c, cudaStream_t st) {
       PSFM_CUDA(cudaFuncSetAttribute(k_band_chol<BSV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = smem;                                                                                                 \
     }                                                                                                              \
-    k_band_chol<BSV, MT><<<1, threads, smem, st>>>(c);                                                              \
+    k_band_chol<BSV, MT><<<grid, threads, smem, st>>>(c);                                                           \
   } while (0)
   if (threads <= 512) PSFM_BC_GO(4, 512);
   else PSFM_BC_GO(4, 1024);

@@ -228,7 +228,13 @@ __device__ __forceinline__ void tile_reduce_points(const TileSmem<TILE>& sm, con
     const int l = pair / nv, k = pair - l * nv;       // component fastest: conflict-free rows, see PSFM_SVS
     const double* row = sm.sv + k * PSFM_SVS;
     double acc = 0.0;
-    for (int e = sm.pstart[l]; e < sm.pstart[l + 1]; ++e) acc += row[e];
+    int e = sm.pstart[l];
+    const int e1 = sm.pstart[l + 1];
+    for (; e + 4 <= e1; e += 4) {
+      const double v0 = row[e], v1 = row[e + 1], v2 = row[e + 2], v3 = row[e + 3];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; e < e1; ++e) acc += row[e];
     fn(k, l, acc);
   }
 }
@@ -240,7 +246,15 @@ __device__ __forceinline__ void tile_reduce_images(const TileSmem<TILE>& sm, con
     const int s = pair / nv, k = pair - s * nv;       // component fastest; perm[e] is a broadcast
     const double* row = sm.sv + k * PSFM_SVS;
     double acc = 0.0;
-    for (int e = sm.coff[s]; e < sm.coff[s + 1]; ++e) acc += row[sm.perm[e]];
+    // same order of additions as the plain loop; four loads in flight instead of one dependent pair per element
+    int e = sm.coff[s];
+    const int e1 = sm.coff[s + 1];
+    for (; e + 4 <= e1; e += 4) {
+      const int i0 = sm.perm[e], i1 = sm.perm[e + 1], i2 = sm.perm[e + 2], i3 = sm.perm[e + 3];
+      const double v0 = row[i0], v1 = row[i1], v2 = row[i2], v3 = row[i3];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; e < e1; ++e) acc += row[sm.perm[e]];
     fn(k, sm.cimg[s], acc);
   }
 }

@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(128) k_schur_pairs(const PairArgs a) {
 // tile kernels.
 
 constexpr int NVX2 = 27;   // NVX (21) | -(W w^) rot (3) | t (3)
-constexpr int PS = 19;     // shared-memory stride of one observation's record (18 doubles + 1 pad)
+constexpr int PS = 18;     // shared-memory stride of one observation's record: 9 x 16 bytes, read with LDS.128 — eight
+                           // consecutive records tile the 32 banks, so the records of one point (consecutive) do not collide
 
 struct StArgs {
   Lin L;
@@ -257,6 +258,24 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
                                                 const double a12, const int rep, const int t0, const int nt) {
   const int tid = threadIdx.x;
   const double inv_f = (a.intr >= 1) ? 1.0 / __ldg(a.K) : 0.0;
+  // Pair tasks of this tile -> lanes: two lanes share a task (q = 2 task + part; entries e0 + part, stride 2).
+  // Measured and dropped (round 2, profiles/r02_schur_tile_notes.md): runs cut into units of <= 8 entries so that
+  // all 8 warps carry pairs (more REDs: 1.11 -> 1.88 ms), three lanes per task (7 trips instead of 11 on the
+  // tile's critical path: 0.98 -> 1.05 ms) — the pair loop is bound by its fp64 instruction count, not by the
+  // longest lane.
+  constexpr int lpt = 2;
+  const int nq = (a.dbg & 2) ? 0 : 2 * nt;
+  auto lane_task = [&](int q, int& tq, int& par) -> bool {
+    par = q & 1; tq = q >> 1;
+    return q < nq;
+  };
+  // the first pass's task range / slot are fetched NOW: two dependent global loads (range, then entries)
+  // would otherwise sit on the critical path of every tile right after the last barrier
+  int tq_f, par_f;
+  const bool valid_f = lane_task(tid, tq_f, par_f);
+  int2 rg_f = make_int2(0, 0);
+  int slot_f = 0;
+  if (valid_f) { rg_f = __ldg(a.task_rng + t0 + tq_f); slot_f = __ldg(a.task_slot + t0 + tq_f); }
   double* sv = sm.sv + tid;
 #pragma unroll
   for (int k = 0; k < NVX2; ++k) sv[k * PSFM_SVS] = 0.0;
@@ -330,36 +349,61 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     });
   }
   __syncthreads();
+  // first entries of the first pass (three in flight per lane: one trip is shorter than an L2 round trip)
+  unsigned int uf0 = 0u, uf1 = 0u, uf2 = 0u;
+  {
+    const int e = rg_f.x + par_f;
+    if (e < rg_f.y) uf0 = __ldg(a.entries + e);
+    if (e + lpt < rg_f.y) uf1 = __ldg(a.entries + e + lpt);
+    if (e + 2 * lpt < rg_f.y) uf2 = __ldg(a.entries + e + 2 * lpt);
+  }
   // the reduction rows are dead: the same shared memory now holds the per-observation records
   double* srec = sm.sv;
   if (act) {
-    double* o = srec + (size_t)tid * PS;
+    double2* o = reinterpret_cast<double2*>(srec + (size_t)tid * PS);
 #pragma unroll
-    for (int k = 0; k < 18; ++k) o[k] = rec[k];
+    for (int k = 0; k < 9; ++k) o[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
   }
   __syncthreads();
   double* band = a.Sband + (size_t)(rep & a.nrep_mask) * a.band_stride;
   // Pair tasks.  Block(i, j) = (W_i H~) W_j' = Jc_i' M Jc_j with the 2x2 M = Q_i Jp_j': per
-  // entry 24 shared-memory loads (the kernel is bound by shared-memory wavefronts, not by the
-  // fp64 pipe) and ~110 flops.  Two lanes per task (even | odd entries), the full 6x6 block in
+  // entry 12 16-byte shared-memory loads (ncu, round 2: 64 % of the L1 data-pipe cycles with 24 8-byte loads at a
+  // 19-double stride, the busiest unit of the kernel) and ~110 flops.  Two lanes per task (even | odd entries), the full 6x6 block in
   // registers, one shuffle per element to combine, 18 REDs per lane.  Uniform trip count.
-  const int nq = (a.dbg & 2) ? 0 : 2 * nt;
   for (int q0 = 0; q0 < nq; q0 += TILE) {
-    const int q = q0 + tid;
-    const bool valid = q < nq;
-    const int t = t0 + (q >> 1), par = q & 1;
-    int e0 = 0, e1 = 0;
-    if (valid) { const int2 rg = __ldg(a.task_rng + t); e0 = rg.x; e1 = rg.y; }
+    int tq = tq_f, par = par_f, e0 = rg_f.x, e1 = rg_f.y, slot = slot_f;
+    bool valid = valid_f;
+    unsigned int u0 = uf0, u1 = uf1, u2 = uf2;
+    if (q0 > 0) {
+      valid = lane_task(q0 + tid, tq, par);
+      e0 = e1 = 0; u0 = u1 = u2 = 0u;
+      if (valid) {
+        const int2 rg = __ldg(a.task_rng + t0 + tq);
+        slot = __ldg(a.task_slot + t0 + tq);
+        e0 = rg.x; e1 = rg.y;
+        const int e = e0 + par;
+        if (e < e1) u0 = __ldg(a.entries + e);
+        if (e + lpt < e1) u1 = __ldg(a.entries + e + lpt);
+        if (e + 2 * lpt < e1) u2 = __ldg(a.entries + e + 2 * lpt);
+      }
+    }
     double acc[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-    int e = e0 + par;
-    unsigned int u_next = (e < e1) ? __ldg(a.entries + e) : 0u;
-    for (; e < e1; e += 2) {
-      const unsigned int u = u_next;
-      if (e + 2 < e1) u_next = __ldg(a.entries + e + 2);
-      const double* Ci = srec + (size_t)(u >> 16) * PS;
-      const double* Cj = srec + (size_t)(u & 0xffffu) * PS;
+    for (int e = e0 + par; e < e1; e += lpt) {
+      const unsigned int u = u0;
+      u0 = u1; u1 = u2;
+      u2 = (e + 3 * lpt < e1) ? __ldg(a.entries + e + 3 * lpt) : 0u;
+      const double2* Pi = reinterpret_cast<const double2*>(srec + (size_t)(u >> 16) * PS);
+      const double2* Pj = reinterpret_cast<const double2*>(srec + (size_t)(u & 0xffffu) * PS);
+      // 12 LDS.128 per entry: [a00 a02 | a12 w0 | w1 w2 | Q (3 x 16 B)] of i, [a00 a02 | a12 w0 | w1 w2 | Jp (3 x 16 B)] of j
+      double Ci[12], Cj[18];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double2 x = Pi[k]; Ci[2 * k] = x.x; Ci[2 * k + 1] = x.y; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const double2 x = Pj[k]; Cj[2 * k] = x.x; Cj[2 * k + 1] = x.y; }
+#pragma unroll
+      for (int k = 6; k < 9; ++k) { const double2 x = Pj[k]; Cj[2 * k] = x.x; Cj[2 * k + 1] = x.y; }
       // M = Q_i Jp_j'
       double m00 = 0.0, m01 = 0.0, m10 = 0.0, m11 = 0.0;
 #pragma unroll
@@ -367,53 +411,65 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
         const double qa = Ci[6 + k], qb = Ci[9 + k], pa = Cj[12 + k], pb = Cj[15 + k];
         m00 = fma(qa, pa, m00); m01 = fma(qa, pb, m01); m10 = fma(qb, pa, m10); m11 = fma(qb, pb, m11);
       }
-      // T = M Jc_j  (2 x 6)
-      double T0[6], T1[6];
+      // The camera Jacobian of an observation is Jc = [Jr | Jt] with Jt = [[a, 0, b], [0, a, c]] (a00, a02, a12)
+      // and the rows of Jr twice the cross products w x (row of Jt), i.e. Jr' = 2 [w]x Jt'.  With
+      // N = Jt_i' M Jt_j (3 x 3), u = w_i, v = w_j the 6 x 6 block is
+      //     tt = N      rt = 2 [u]x N      tr = 2 B      rr = 4 [u]x B,     B[r, :] = v x N[r, :]
+      // — 104 fp64 instructions per entry instead of 144 for the products with the explicit 2 x 6 Jacobians
+      // (the fp64 pipe is what bounds this loop); the factors 2 and 4 are applied once per task.
+      double N[3][3];
       {
-        const double b00 = Cj[0], b02 = Cj[1], b12 = Cj[2];
-        double j0[6], j1[6];
-        if (ROT) {
-          const double w0 = Cj[3], w1 = Cj[4], w2 = Cj[5];
-          j0[0] = 2.0 * b02 * w1; j0[1] = 2.0 * (b00 * w2 - b02 * w0); j0[2] = -2.0 * b00 * w1;
-          j1[0] = 2.0 * (b12 * w1 - b00 * w2); j1[1] = -2.0 * b12 * w0; j1[2] = 2.0 * b00 * w0;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) { j0[k] = 0.0; j1[k] = 0.0; }
-        }
-        j0[3] = b00; j0[4] = 0.0; j0[5] = b02;
-        j1[3] = 0.0; j1[4] = b00; j1[5] = b12;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { T0[c] = m00 * j0[c] + m01 * j1[c]; T1[c] = m10 * j0[c] + m11 * j1[c]; }
+        const double aj = Cj[0], bj = Cj[1], cj = Cj[2], ai = Ci[0], bi = Ci[1], ci = Ci[2];
+        const double t00 = m00 * aj, t01 = m01 * aj, t02 = fma(m01, cj, m00 * bj);
+        const double t10 = m10 * aj, t11 = m11 * aj, t12 = fma(m11, cj, m10 * bj);
+        N[0][0] = ai * t00; N[0][1] = ai * t01; N[0][2] = ai * t02;
+        N[1][0] = ai * t10; N[1][1] = ai * t11; N[1][2] = ai * t12;
+        N[2][0] = fma(ci, t10, bi * t00); N[2][1] = fma(ci, t11, bi * t01); N[2][2] = fma(ci, t12, bi * t02);
       }
-      // acc += Jc_i' T
-      {
-        const double c00 = Ci[0], c02 = Ci[1], c12 = Ci[2];
-        double i0[6], i1[6];
-        if (ROT) {
-          const double w0 = Ci[3], w1 = Ci[4], w2 = Ci[5];
-          i0[0] = 2.0 * c02 * w1; i0[1] = 2.0 * (c00 * w2 - c02 * w0); i0[2] = -2.0 * c00 * w1;
-          i1[0] = 2.0 * (c12 * w1 - c00 * w2); i1[1] = -2.0 * c12 * w0; i1[2] = 2.0 * c00 * w0;
-        } else {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) { i0[k] = 0.0; i1[k] = 0.0; }
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[6 * (3 + r) + 3 + c] += N[r][c];
+      if (ROT) {
+        const double u0 = Ci[3], u1 = Ci[4], u2 = Ci[5], v0 = Cj[3], v1 = Cj[4], v2 = Cj[5];
+        double B[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          B[r][0] = fma(v1, N[r][2], -(v2 * N[r][1]));
+          B[r][1] = fma(v2, N[r][0], -(v0 * N[r][2]));
+          B[r][2] = fma(v0, N[r][1], -(v1 * N[r][0]));
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[6 * (3 + r) + c] += B[r][c];                       // tr / 2
         }
-        i0[3] = c00; i0[4] = 0.0; i0[5] = c02;
-        i1[3] = 0.0; i1[4] = c00; i1[5] = c12;
 #pragma unroll
-        for (int r = (ROT ? 0 : 3); r < 6; ++r)
-#pragma unroll
-          for (int c = (ROT ? 0 : 3); c < 6; ++c) acc[6 * r + c] = fma(i1[r], T1[c], fma(i0[r], T0[c], acc[6 * r + c]));
+        for (int k = 0; k < 3; ++k) {
+          // rt / 2: column k of [u]x N;   rr / 4: column k of [u]x B
+          acc[6 * 0 + 3 + k] = fma(u1, N[2][k], fma(-u2, N[1][k], acc[6 * 0 + 3 + k]));
+          acc[6 * 1 + 3 + k] = fma(u2, N[0][k], fma(-u0, N[2][k], acc[6 * 1 + 3 + k]));
+          acc[6 * 2 + 3 + k] = fma(u0, N[1][k], fma(-u1, N[0][k], acc[6 * 2 + 3 + k]));
+          acc[6 * 0 + k] = fma(u1, B[2][k], fma(-u2, B[1][k], acc[6 * 0 + k]));
+          acc[6 * 1 + k] = fma(u2, B[0][k], fma(-u0, B[2][k], acc[6 * 1 + k]));
+          acc[6 * 2 + k] = fma(u0, B[1][k], fma(-u1, B[0][k], acc[6 * 2 + k]));
+        }
       }
     }
+    if (ROT) {
 #pragma unroll
-    for (int k = 0; k < 36; ++k)
-      if (ROT || (k / 6 >= 3 && k % 6 >= 3)) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-    if (valid && !(a.dbg & 1)) {
-      double* dst = band + (size_t)__ldg(a.task_slot + t) * 36 + 18 * par;
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int k = 0; k < 18; ++k) {
-        const double v = par ? acc[18 + k] : acc[k];
-        if (ROT || v != 0.0) atomicAdd(dst + k, v);      // rotation blocks are structurally zero without ROT
+        for (int c = 0; c < 3; ++c) { acc[6 * r + c] *= 4.0; acc[6 * r + 3 + c] *= 2.0; acc[6 * (3 + r) + c] *= 2.0; }
+    }
+    // combine the lanes of a task: lane `par` ends up with the sums of ITS share of the 36 elements (every
+    // lane sends what its reader owns), then one RED per element
+    double* dst = band + (size_t)slot * 36;
+    const bool red = valid && !(a.dbg & 1);
+    {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) {
+        const double mine = par ? acc[18 + i] : acc[i];
+        const double x = par ? acc[i] : acc[18 + i];
+        const double v = mine + __shfl_xor_sync(0xffffffffu, x, 1);
+        if (red && (ROT || v != 0.0)) atomicAdd(dst + 18 * par + i, v);
       }
     }
   }
@@ -513,7 +569,7 @@ __global__ void k_unit_count(const int* ucount, int nruns, int chunk, int* nunit
 // units of a tile are processed longest first (lanes of a warp then run similar trip counts and the
 // short units fill the last pass): sort key (tile, ~count), payload = (slot, entry range)
 __global__ void k_unit_fill(const unsigned long long* ukeys, const int* ucount, const int* beg, const int* ubeg, int nruns,
-                            int fbits, int span, unsigned long long* key2, int* idx, int* slot, int2* rng) {
+                            int fbits, int span, int by_pair, unsigned long long* key2, int* idx, int* slot, int2* rng) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nruns) return;
   const unsigned long long k = ukeys[t], mask = (1ull << fbits) - 1;
@@ -523,7 +579,7 @@ __global__ void k_unit_fill(const unsigned long long* ukeys, const int* ucount, 
   int e = beg[t];
   for (int c = 0; c < n; ++c) {
     const int len = base + (c < rem), u = ubeg[t] + c;
-    key2[u] = (tile << 32) | (unsigned long long)(0xffffffffu - (unsigned)len);
+    key2[u] = (tile << 32) | (by_pair ? (unsigned long long)(unsigned)u : (unsigned long long)(0xffffffffu - (unsigned)len));
     idx[u] = u;
     slot[u] = a * (span + 1) + (b - a);
     rng[u] = make_int2(e, e + len);

@@ -164,8 +164,7 @@ struct psfm_ba_solver {
   DBuf<double> d_xband, d_bandrep;      // d_xband = [xcam F*NVX2 | Sband band_n] (one all-reduce)
   // single-CTA sliding-window band Cholesky (ba_band_chol.cuh): compact band matrix, factor, scratch
   bool band_chol = false;
-  int bcW = 0, bcBw = 0, bcRows = 0;
-  DBuf<double> d_Ab, d_C4, d_Lr, d_La, d_dinv;
+  BandWork bwk;             // plan + buffers of k_band_chol
   DBuf<PcgState> d_pcg;
   HostScalars* hs = nullptr;
   double* pin_state = nullptr;     // pinned staging of the state: pose (8F) | X (3P) | K (3C)
@@ -866,21 +865,13 @@ __global__ void k_point_span(const int* pt_ptr, const int* obs_img, int P, int* 
 // The fused path ends in Sband: when the band is narrow enough for the register window of
 // k_band_chol, the reduced system never exists as a dense matrix.
 void setup_band_chol(psfm_ba_solver* S) {
-  const int nb = 6 * S->F;
-  const int bw = std::min(S->bw, nb - 1);
-  const int W = band_chol_window(bw);
-  S->band_chol = S->fused && W > 0 && !getenv("PSFM_OLD_CHOL");
+  const BandPlan pl = band_chol_plan(6 * S->F, S->bw);
+  S->band_chol = S->fused && pl.W > 0 && !getenv("PSFM_OLD_CHOL");
   if (!S->band_chol) {
     S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), S->stream);
     return;
   }
-  S->bcW = W; S->bcBw = bw;
-  S->bcRows = band_chol_rows(nb, W);
-  S->d_Ab.alloc((size_t)S->bcRows * (W + 4), S->stream);
-  S->d_C4.alloc(16, S->stream);
-  S->d_Lr.alloc((size_t)nb * (bw + 1), S->stream); S->d_Lr.zero(S->stream);
-  S->d_La.alloc(4 * (size_t)nb, S->stream);
-  S->d_dinv.alloc(nb, S->stream);
+  S->bwk.alloc(pl, S->stream);
 }
 
 // (i, j) observation pairs of every point grouped by image pair — built once per problem
@@ -1002,8 +993,9 @@ void ensure_pairs(psfm_ba_solver* S) {
     PSFM_CUDA(cudaMemcpyAsync(&nr, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PSFM_CUDA(cudaStreamSynchronize(st));
     // runs -> units of <= chunk entries (k_unit_count / k_unit_fill)
-    int chunk = 8;
+    int chunk = 1 << 30;
     if (const char* e = getenv("PSFM_TASK_CHUNK")) chunk = std::max(1, atoi(e));
+    const int by_pair = getenv("PSFM_TASK_BY_LENGTH") ? 0 : 1;
     DBuf<int> beg0, nun, ubeg;
     beg0.alloc((size_t)nr + 1, st); nun.alloc((size_t)nr + 1, st); ubeg.alloc((size_t)nr + 1, st);
     PSFM_CUDA(cudaMemsetAsync(ucount.p + nr, 0, sizeof(int), st));
@@ -1026,7 +1018,7 @@ void ensure_pairs(psfm_ba_solver* S) {
     DBuf<unsigned long long> key2, key2_out;
     slot0.alloc(nt, st); rng0.alloc(nt, st); idx0.alloc(nt, st); order.alloc(nt, st); key2.alloc(nt, st); key2_out.alloc(nt, st);
     if (nt) {
-      k_unit_fill<<<grid_for(nr), 256, 0, st>>>(uk64.p, ucount.p, beg0.p, ubeg.p, nr, fb, S->span, key2.p, idx0.p, slot0.p, rng0.p);
+      k_unit_fill<<<grid_for(nr), 256, 0, st>>>(uk64.p, ucount.p, beg0.p, ubeg.p, nr, fb, S->span, by_pair, key2.p, idx0.p, slot0.p, rng0.p);
       PSFM_LAUNCH_CHECK();
       size_t need = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, need, key2.p, key2_out.p, idx0.p, order.p, nt, 0, 32 + tb, st);
@@ -1161,20 +1153,18 @@ void launch_cholesky(psfm_ba_solver* S) {
 // factor, solve -> d_x; d_cholfail[0] = 1 on a bad pivot
 void launch_band_cholesky(psfm_ba_solver* S) {
   cudaStream_t st = S->stream;
-  const int nb = 6 * S->F, W = S->bcW, bw = S->bcBw, RS = W + 4;
+  const BandPlan& pl = S->bwk.pl;
   BandAsmArgs2 b;
   b.Sband = S->d_xband.p + (size_t)S->F * NVX2;
   b.lin_cam = S->d_lin.p; b.lin_intr = S->d_lin.p + (size_t)S->F * NVL;
   b.prep_intr = S->d_prep.p + (size_t)S->F * NVL;
   b.xcam = S->d_xband.p; b.xstride = NVX2;
   b.scale_c = S->d_scale_c.p; b.Dc2 = S->d_Dc2.p; b.rhs = S->d_rhs.p; b.active = S->d_active.p;
-  b.F = S->F; b.span = S->span; b.nb = nb; b.bw = bw; b.W = W; b.RS = RS; b.nrows = S->bcRows;
-  b.Ab = S->d_Ab.p; b.C4 = S->d_C4.p;
-  k_band_assemble<<<grid_for((size_t)S->bcRows * RS), 256, 0, st>>>(b);
+  b.F = S->F; b.span = S->span; b.pl = pl;
+  b.Ab = S->bwk.ab(0); b.Ab1 = S->bwk.ab(1); b.C4 = S->bwk.C4.p; b.fail = S->d_cholfail.p;
+  k_band_assemble<<<grid_for((size_t)(pl.rows[0] + pl.rows[1]) * pl.RS), 256, 0, st>>>(b);
   PSFM_LAUNCH_CHECK();
-  BandCholArgs c;
-  c.Ab = S->d_Ab.p; c.C4 = S->d_C4.p; c.nb = nb; c.bw = bw; c.W = W; c.RS = RS; c.ns = S->NS;
-  c.Lr = S->d_Lr.p; c.La = S->d_La.p; c.dinv = S->d_dinv.p; c.x = S->d_x.p; c.fail = S->d_cholfail.p;
+  BandCholArgs c = S->bwk.args(S->d_x.p, S->NS, S->d_cholfail.p);
   static const bool want_prof = getenv("PSFM_CHOL_PROFILE") != nullptr;
   if (want_prof && S->d_cholprof.n < 16) { S->d_cholprof.alloc(16, st); S->d_cholprof.zero(st); }
   c.prof = want_prof ? reinterpret_cast<long long*>(S->d_cholprof.p) : nullptr;
@@ -1962,16 +1952,33 @@ extern "C" int psfm_ba_band_solve(const double* A, const double* b, int32_t nb, 
   int rc = check_device();
   if (rc != PSFM_OK) return rc;
   bw = std::min(bw, nb - 1);
-  const int W = band_chol_window(bw), RS = W + 4, n = nb + 3;
+  const BandPlan pl = band_chol_plan(nb, bw);
+  const int W = pl.W, RS = pl.RS, n = nb + 3;
   if (W == 0) { set_error("psfm_ba_band_solve: band too wide for the register window"); return PSFM_ERR_UNSUPPORTED; }
-  const int nrows = band_chol_rows(nb, W);
-  std::vector<double> Ab((size_t)nrows * RS, 0.0), C4(16, 0.0);
-  for (int r = 0; r < nrows; ++r) {
+  bw = pl.bw;
+  // the layout k_band_assemble writes, from the dense input (both sides of the two-sided form)
+  auto entry = [&](int R, int e) -> double {            // A[R][R - e], identity below nb
+    if (R >= nb) return e == 0 ? 1.0 : 0.0;
+    return A[(size_t)R * n + (R - e)];
+  };
+  auto arrow = [&](int R, int aa) -> double {
+    if (R >= nb) return 0.0;
+    return aa < 3 ? A[(size_t)(nb + aa) * n + R] : b[R];
+  };
+  std::vector<double> Ab((size_t)(pl.rows[0] + pl.rows[1]) * RS, 0.0), C4(32, 0.0);
+  for (int r = 0; r < pl.rows[0]; ++r) {
     double* row = &Ab[(size_t)r * RS];
-    if (r >= nb) { row[0] = 1.0; continue; }
-    for (int k = 0; k <= std::min(bw, r); ++k) row[k] = A[(size_t)r * n + (r - k)];
-    for (int a = 0; a < 3; ++a) row[W + a] = A[(size_t)(nb + a) * n + r];
-    row[W + 3] = b[r];
+    if (r >= std::min((int)nb, pl.nbs[0])) { row[0] = 1.0; continue; }
+    for (int k = 0; k <= std::min((int)bw, r); ++k) row[k] = entry(r, k);
+    for (int a = 0; a < 4; ++a) row[W + a] = arrow(r, a);
+  }
+  for (int r = 0; r < pl.rows[1]; ++r) {
+    double* row = &Ab[(size_t)(pl.rows[0] + r) * RS];
+    if (r >= pl.nbs[1]) { row[0] = 1.0; continue; }
+    for (int k = 0; k <= std::min((int)bw, r); ++k)
+      if (!(r >= pl.n1 && r - k >= pl.n1)) row[k] = entry(pl.nbp - 1 - (r - k), k);
+    if (r < pl.n1)
+      for (int a = 0; a < 4; ++a) row[W + a] = arrow(pl.nbp - 1 - r, a);
   }
   for (int a = 0; a < 3; ++a) {
     for (int c = 0; c < 3; ++c) C4[4 * a + c] = A[(size_t)(nb + a) * n + nb + c];
@@ -1979,14 +1986,12 @@ extern "C" int psfm_ba_band_solve(const double* A, const double* b, int32_t nb, 
   }
   try {
     cudaStream_t st = nullptr;
-    DBuf<double> dAb, dC4, dLr, dLa, dinv, dx;
+    BandWork wk;
+    DBuf<double> dx;
     DBuf<int> dfail;
-    dAb.alloc(Ab.size()); dC4.alloc(16); dLr.alloc((size_t)nb * (bw + 1)); dLa.alloc(4 * (size_t)nb); dinv.alloc(nb); dx.alloc(n); dfail.alloc(1);
-    dAb.upload(Ab.data(), Ab.size(), st); dC4.upload(C4.data(), 16, st); dLr.zero(st);
-    BandCholArgs c;
-    c.Ab = dAb.p; c.C4 = dC4.p; c.nb = nb; c.bw = bw; c.W = W; c.RS = RS; c.ns = n;
-    c.Lr = dLr.p; c.La = dLa.p; c.dinv = dinv.p; c.x = dx.p; c.fail = dfail.p;
-    c.prof = nullptr;
+    wk.alloc(pl, st); dx.alloc(n); dfail.alloc(1); dfail.zero(st);
+    wk.Ab.upload(Ab.data(), Ab.size(), st); wk.C4.upload(C4.data(), 32, st);
+    BandCholArgs c = wk.args(dx.p, n, dfail.p);
     band_chol_launch(c, st);
     int fail = 0;
     PSFM_CUDA(cudaMemcpy(&fail, dfail.p, sizeof(int), cudaMemcpyDeviceToHost));

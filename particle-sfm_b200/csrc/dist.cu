@@ -70,7 +70,7 @@ int rank() { return g.rank; }
 // the same order on every rank, so the replicated results are bit-identical across ranks — and writes
 // the result over the local operand.  Two parities make the buffer of epoch k safe to overwrite in epoch
 // k+2: passing the barrier of epoch k+1 means every peer has finished reading epoch k.  A wait that
-// exceeds ~2 s sets p2p_error (no hang on a dead peer).  Falls back to NCCL when IPC set-up fails or
+// exceeds ~60 s sets the error flag (no hang on a dead peer).  Falls back to NCCL when IPC set-up fails or
 // PSFM_NO_P2P is set.
 constexpr int P2P_MAX_WORLD = 16;
 constexpr size_t P2P_BYTES = (size_t)8 << 20;       // per parity; operands above this go through NCCL
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) k_p2p_reduce(double* __restrict__ out, si
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1ull); break; }     // ~2 s: a peer never arrived
+      if (clock64() - t0 > 120000000000ll) { atomicExch(err, 1ull); break; }   // ~60 s: a peer never arrived (ranks may be seconds apart)
     }
   }
   __syncthreads();

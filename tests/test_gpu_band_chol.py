@@ -64,3 +64,35 @@ def test_band_solve_inactive_arrow_and_failure(gpu):
     A2, b2 = _system(400, 300, seed=2)                # window would be 304 > 152
     rc, _ = _solve(A2, b2, 400, 300)
     assert rc == -4                     # PSFM_ERR_UNSUPPORTED: wider than the register window
+
+
+@pytest.mark.parametrize("bad", [57, 199, 200, 215, 330, 399])
+def test_two_sided_form_reports_a_bad_pivot_wherever_it_is(gpu, bad):
+    """nb = 400, bw = 35: window 40, two CTAs (top-down 184 pivots, bottom-up 176, 40 in the middle).  A negative
+    diagonal on either side or in the middle must come back as an error, never as a hang or a silent solve."""
+    A, b = _system(400, 35, seed=3)
+    rc, x = _solve(A, b, 400, 35)
+    assert rc == 0
+    ref = np.linalg.solve(A, b)
+    assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
+    A[bad, bad] = -1.0
+    rc, _ = _solve(A, b, 400, 35)
+    assert rc == -1
+
+
+def test_two_sided_and_one_sided_forms_agree(gpu):
+    """PSFM_CHOL_ONE_SIDED is read once per process: run the one-sided form in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path[:0] = [%r, %r]; from test_gpu_band_chol import _system, _solve;"
+            "A, b = _system(1203, 95, seed=9); rc, x = _solve(A, b, 1203, 95); assert rc == 0; np.save(sys.argv[1], x)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for name, env in (("two", {}), ("one", {"PSFM_CHOL_ONE_SIDED": "1"})):
+        path = os.path.join(root, "gpurun_out", f"_band_{name}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests")), path], check=True, env={**os.environ, **env}, cwd=root)
+        out[name] = np.load(path)
+    assert np.abs(out["two"] - out["one"]).max() <= 1e-12 * np.abs(out["one"]).max()
+    assert not np.array_equal(out["two"], out["one"])      # a different elimination order: not the same bits

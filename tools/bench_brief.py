@@ -12,6 +12,10 @@ line = [l for l in out.stdout.splitlines() if l.startswith("{")]
 if not line:
     print(out.stdout[-2000:], out.stderr[-2000:])
     sys.exit(1)
+for l in out.stderr.splitlines():
+    if l.startswith("[psfm"):
+        print(l)
+        break
 d = json.loads(line[-1])
 env = {k: v for k, v in os.environ.items() if k.startswith("PSFM_")}
 print(env, f"ms_per_step {d['ms_per_step']:.3f} its {d['lm_iterations_per_step']} final_cost {d['final_cost']:.6f} units {d.get('pair_units')}")
