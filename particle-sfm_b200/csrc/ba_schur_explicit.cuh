@@ -557,6 +557,12 @@ __global__ void k_pair_fill_tile(const int* pt_ptr, const int* obs_pt, const int
   }
 }
 
+// first entry of every tile (entries are written in observation order, tiles are observation ranges)
+__global__ void k_tile_entry_offsets(const int* tile_start, const int* ptr, int T, int* seg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= T) seg[t] = ptr[tile_start[t]];
+}
+
 // A run of equal keys (one image pair of one tile) is cut into UNITS of at most `chunk` entries, all
 // of (nearly) the same length; a unit is what two lanes of k_schur_tile accumulate in registers.
 // Without the cut the longest run of a tile (every point of the tile sees both images) sets the trip

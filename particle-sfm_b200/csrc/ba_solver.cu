@@ -96,8 +96,13 @@ PinnedPool g_pinned;
 
 struct StreamHolder {   // declared first in the solver => destroyed last (after every DBuf)
   cudaStream_t s = nullptr;
+  cudaStream_t copy = nullptr;      // second H2D queue: the coordinates travel while the index arrays are being sorted
+  cudaEvent_t ev_idx = nullptr, ev_xy = nullptr;
   ~StreamHolder() {
+    if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
     if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (ev_idx) cudaEventDestroy(ev_idx);
+    if (ev_xy) cudaEventDestroy(ev_xy);
   }
 };
 
@@ -234,7 +239,12 @@ int upload_problem(psfm_ba_solver* S, const psfm_ba_problem* pb) {
   S->d_img_cam.alloc(F, st); S->d_img_cam.upload(S->image_camera.data(), F, st);
   S->d_in_img.alloc(M, st); S->d_in_pt.alloc(M, st); S->d_in_xy.alloc(M, st); S->d_alive.alloc(M, st);
   S->d_in_img.upload(pb->obs_image, M, st); S->d_in_pt.upload(pb->obs_point, M, st);
-  S->d_in_xy.upload(reinterpret_cast<const double2*>(pb->obs_xy), M, st);
+  // the coordinates (half of the bytes) follow on the copy queue: counting, ordering and sorting need the
+  // indices only, k_st_gather waits for ev_xy
+  PSFM_CUDA(cudaEventRecord(S->sh.ev_idx, st));
+  PSFM_CUDA(cudaStreamWaitEvent(S->sh.copy, S->sh.ev_idx, 0));
+  S->d_in_xy.upload(reinterpret_cast<const double2*>(pb->obs_xy), M, S->sh.copy);
+  PSFM_CUDA(cudaEventRecord(S->sh.ev_xy, S->sh.copy));
   PSFM_CUDA(cudaMemsetAsync(S->d_alive.p, 1, (size_t)(M ? M : 1), st));
   S->d_count.alloc(1, st);
   return PSFM_OK;
@@ -258,6 +268,7 @@ int build_structure(psfm_ba_solver* S) {
   const int* in_pt_p = S->d_in_pt.p;
   const double2* in_xy_p = S->d_in_xy.p;
   if (S->num_alive != S->M0) {
+    PSFM_CUDA(cudaStreamWaitEvent(st, S->sh.ev_xy, 0));
     // stream compaction of the alive observations (index select + gather)
     DBuf<int> iota, nsel;
     iota.alloc(S->M0, st); sel.alloc(S->M0, st); nsel.alloc(1, st);
@@ -326,6 +337,7 @@ int build_structure(psfm_ba_solver* S) {
     k_st_keys<<<grid_for(M), 256, 0, st>>>(in_img_p, in_pt_p, pt_new.p, M, keys.p, idx.p); PSFM_LAUNCH_CHECK();
     need = tmp_bytes + 256;
     cub::DeviceRadixSort::SortPairs(tmp.p, need, keys.p, keys_out.p, idx.p, S->d_obs_orig.p, M, 0, 32 + pbits, st);
+    PSFM_CUDA(cudaStreamWaitEvent(st, S->sh.ev_xy, 0));
     k_st_gather<<<grid_for(M), 256, 0, st>>>(keys_out.p, S->d_obs_orig.p, in_xy_p, M, S->d_obs_img.p, S->d_obs_pt.p, S->d_obs_xy.p);
     PSFM_LAUNCH_CHECK();
     if (sel.n) { k_compose_index<<<grid_for(M), 256, 0, st>>>(S->d_obs_orig.p, sel.p, M); PSFM_LAUNCH_CHECK(); }   // -> caller's index
@@ -976,10 +988,15 @@ void ensure_pairs(psfm_ba_solver* S) {
                                                    S->d_tile_start.p, T, fb, k64.p, v32.p);
     PSFM_LAUNCH_CHECK();
     {
+      // k_pair_fill_tile writes the entries in observation order, i.e. already tile by tile: what is left is a
+      // sort of each tile's ~1.6 k entries by their image pair (the low 2 fb bits) — one pass through shared
+      // memory per tile instead of four passes of a global 64-bit radix sort over 39 M pairs
+      DBuf<int> seg; seg.alloc((size_t)T + 1, st);
+      k_tile_entry_offsets<<<grid_for((size_t)T + 1), 256, 0, st>>>(S->d_tile_start.p, ptr32.p, T, seg.p); PSFM_LAUNCH_CHECK();
       size_t need = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, 0, tb + 2 * fb, st);
+      cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, T, seg.p, seg.p + 1, 0, 2 * fb, st);
       DBuf<unsigned char> tmp; tmp.alloc(need + 256, st);
-      cub::DeviceRadixSort::SortPairs(tmp.p, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, 0, tb + 2 * fb, st);
+      cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, need, k64.p, k64_out.p, v32.p, S->d_tentries.p, (int)NPr, T, seg.p, seg.p + 1, 0, 2 * fb, st);
     }
     k64.release(); v32.release();
     uk64.alloc(NPr, st); ucount.alloc(NPr + 1, st); nruns.alloc(1, st);
@@ -1598,6 +1615,9 @@ extern "C" int psfm_ba_create(const psfm_ba_problem* pb, psfm_ba_solver** out) {
   psfm_ba_solver* S = new psfm_ba_solver();
   try {
     PSFM_CUDA(cudaStreamCreateWithFlags(&S->sh.s, cudaStreamNonBlocking));
+    PSFM_CUDA(cudaStreamCreateWithFlags(&S->sh.copy, cudaStreamNonBlocking));
+    PSFM_CUDA(cudaEventCreateWithFlags(&S->sh.ev_idx, cudaEventDisableTiming));
+    PSFM_CUDA(cudaEventCreateWithFlags(&S->sh.ev_xy, cudaEventDisableTiming));
     S->stream = S->sh.s;
     rc = upload_problem(S, pb);
     if (rc == PSFM_OK) rc = build_structure(S);
