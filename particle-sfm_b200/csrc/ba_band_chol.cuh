@@ -57,6 +57,7 @@ constexpr int BC_MAXSLOT = 7;     // 1 + ceil(bw / 32) register slots of the bac
 struct BandPlan {
   int nb, bw, W, RS;
   int two;                  // 1: two CTAs
+  int blk6;                 // 1: block-6 kernel k_band_chol6 (nb and bw + 1 multiples of 6, 3 <= W / 6 <= 25)
   int nbp;                  // nb rounded up to 8 (identity padding rows)
   int k0, n1;               // pivots factored top-down before the hand-over | bottom-up; k0 + W + n1 = nbp
   int nbs[2];               // rows of the matrix each side sees: k0 + W | n1 + W   (one-sided: nb | 0)
@@ -185,6 +186,7 @@ struct BandCholArgs {
   double* D;                // hand-over of side 1: [W][W] update of the middle block (A orientation) | [4][W] arrow | [16] corner
   int* sync;                // [2] = epoch once: 0 the hand-over is written, 1 the middle x and the intrinsics are written
   int epoch;
+  int blk6;                 // k_band_chol6 (plan)
   int flags;                // timing experiments (PSFM_CHOL_FLAGS; results invalid): 1 no output of L, 2 no reciprocal, 4 no publish, 8 barrier + pivot load only, 16 no row streaming
   long long* prof;          // optional [8]: SM cycles of factorisation | corner + staging | back substitution, pivots (side 0)
 };
@@ -219,6 +221,155 @@ __device__ __forceinline__ double bc_rcp(double d) {
   return fma(r, e, r);
 }
 
+// Everything after the factorisation, shared by k_band_chol and k_band_chol6: normalisation, the 3 x 3 arrow corner
+// (s_c4: the 4 x 4 corner block of the window, written to shared memory by its owner before the caller's barrier),
+// hand-shake of the two-sided form, back substitution.  Called by every thread of the CTA.
+template <int RP>
+__device__ __forceinline__ void bc_tail(const BandCholArgs& a, const BandSide& sd, const int side, double* stage, int& s_fail,
+                                        double* s_xI, const double* s_c4, const long long tk0, const long long tk1) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nb = sd.nb, npiv = sd.npiv, bw = a.bw, LS = bw + 1;
+  const int nsteps = npiv;
+  // 1 / sqrt(d): normalisation of the stored columns, applied while staging the back substitution
+  for (int j = tid; j < npiv; j += blockDim.x) sd.dinv[j] = rsqrt(__ldcg(sd.dinv + j));
+  // ---- arrow corner: 3 x 3 intrinsics block and its right-hand side (thread of block {Wb, Wb})
+  if (side == 0 && tid == 0) {
+    bool cbad = false;
+    const double m00 = s_c4[0], m10 = s_c4[4], m20 = s_c4[8], m11 = s_c4[5], m21 = s_c4[9], m22 = s_c4[10];
+    cbad |= !(m00 > 0.0);
+    const double l00 = sqrt(m00), l10 = m10 / l00, l20 = m20 / l00;
+    double t = m11 - l10 * l10;
+    cbad |= !(t > 0.0);
+    const double l11 = sqrt(t), l21 = (m21 - l20 * l10) / l11;
+    t = m22 - l20 * l20 - l21 * l21;
+    cbad |= !(t > 0.0);
+    const double l22 = sqrt(t);
+    const double z0 = s_c4[12] / l00, z1 = (s_c4[13] - l10 * z0) / l11, z2 = (s_c4[14] - l20 * z0 - l21 * z1) / l22;
+    const double x2 = z2 / l22, x1 = (z1 - l21 * x2) / l11, x0 = (z0 - l10 * x1 - l20 * x2) / l00;
+    s_xI[0] = x0; s_xI[1] = x1; s_xI[2] = x2;
+    if (cbad || !isfinite(x0 + x1 + x2)) s_fail = 1;
+  }
+  __syncthreads();
+  if (tid == 0 && s_fail) atomicOr(a.fail, 1);
+  if (side == 0) {
+    if (s_fail) {
+      if (a.two && tid == 0) bc_post(a.sync + 1, a.epoch);     // side 1 must not wait for ever
+      return;
+    }
+    for (int s = a.nbg + tid; s < a.ns; s += blockDim.x) a.x[s] = (s < a.nbg + 3) ? s_xI[s - a.nbg] : 0.0;
+  } else {
+    // the middle x and the intrinsics come from side 0
+    if (tid == 0) {
+      bc_wait(a.sync + 1, a.epoch);
+      for (int k = 0; k < 3; ++k) s_xI[k] = __ldcg(a.x + a.nbg + k);
+    }
+    __syncthreads();
+  }
+
+  // ---- back substitution L' x = y - La' x_I in axpy form (warp 0; the other warps stage).
+  //      Lane l holds the running right-hand side of positions 32 (c - m) + l, m = 0 .. msv-1, of the
+  //      current 32-column chunk c.  stage[jj][32 + k] = -L[r][r - k] for 1 <= k <= bw (r = 32 c + jj),
+  //      zero elsewhere, so the inner step is one shared load and one fma per slot — no predicates;
+  //      per pivot one fma, one shuffle and one fma are on the dependent chain.  Rows >= npiv (side 1:
+  //      the middle rows) are not solved for: their x is known and only propagated.
+  const int ms = 1 + (bw + 31) / 32;
+  const int msv = ms <= 4 ? 4 : BC_MAXSLOT;
+  const int LSP = 32 * (msv + 1);
+  const int ctop = (nb + 31) / 32 - 1;
+  const int cpost = (a.two && side == 0) ? a.k0 / 32 : -1;     // after this chunk every middle x is written
+  const int CH = 32 * LSP;
+  // one row per warp and pass; all loads of a row (<= 7 x 2 per lane) are issued before the first use — with a
+  // dependent load pair per element the staging, not the substitution chain, set the pace (measured: 7.5 k cycles
+  // per 32-row chunk against 1.3 k for the chain)
+  auto stage_chunk = [&](int c, double* buf, int w0, int nw) {
+    // RP rows per pass (2 in the block-6 kernel): with 8 warps (the block-6 kernel) a warp stages ~5 rows of a chunk, one global-memory
+    // latency each would outlast the substitution chain of the chunk
+    for (int j0 = w0; j0 < 32; j0 += RP * nw) {
+      double lv[RP][BC_MAXSLOT], dv[RP][BC_MAXSLOT];
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int jj = j0 + h * nw, r = 32 * c + jj;
+#pragma unroll
+        for (int t = 0; t < BC_MAXSLOT; ++t) {
+          const int k = lane + 32 * t;                       // element q = 32 (t + 1) + lane of the padded row
+          const bool ok = jj < 32 && t < msv && k >= 1 && k <= bw && r < nb && r - k >= 0 && r - k < npiv;
+          lv[h][t] = ok ? __ldcg(sd.Lr + (size_t)r * LS + k) : 0.0;
+          dv[h][t] = ok ? __ldcg(sd.dinv + r - k) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int jj = j0 + h * nw;
+        if (jj < 32) {
+          buf[jj * LSP + lane] = 0.0;
+#pragma unroll
+          for (int t = 0; t < BC_MAXSLOT; ++t)
+            if (t < msv) buf[jj * LSP + 32 * (t + 1) + lane] = -lv[h][t] * dv[h][t];
+        }
+      }
+    }
+  };
+  const double xi0 = s_xI[0], xi1 = s_xI[1], xi2 = s_xI[2];
+  auto y0 = [&](int i) -> double {
+    if (i < 0 || i >= npiv) return 0.0;
+    return __ldcg(sd.dinv + i) * (__ldcg(sd.La + 3 * (size_t)nb + i) -
+           (xi0 * __ldcg(sd.La + i) + xi1 * __ldcg(sd.La + (size_t)nb + i) + xi2 * __ldcg(sd.La + 2 * (size_t)nb + i)));
+  };
+  const int wid = tid >> 5, nwarp = blockDim.x >> 5;
+  stage_chunk(ctop, stage, wid, nwarp);
+  double yy[BC_MAXSLOT];
+#pragma unroll
+  for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = (tid < 32 && m < ms) ? y0(32 * (ctop - m) + lane) : 0.0;
+  __syncthreads();
+  const long long tk2 = a.prof ? clock64() : 0;
+  for (int c = ctop, n = 0; c >= 0; --c, ++n) {
+    const double* buf = stage + (n & 1) * CH;
+    if (tid >= 32) {
+      if (c > 0) stage_chunk(c - 1, stage + ((n + 1) & 1) * CH, wid - 1, nwarp - 1);
+    } else {
+      const double fresh = (c > 0) ? y0(32 * (c - ms) + lane) : 0.0;     // slot ms - 1 of the next chunk
+      const int jl = 32 * c + lane;
+      const double dl = (jl < npiv) ? __ldcg(sd.dinv + jl) : 0.0;
+      // global index of local row jl: side 0 jl, side 1 nbp - 1 - jl; rows past nbg are identity padding (x = 0)
+      const int gl = side ? a.nbp - 1 - jl : jl;
+      const bool inx = jl < nb && gl >= 0 && gl < a.nbg;
+      const double xk = (jl >= npiv && inx) ? __ldcg(a.x + gl) : 0.0;   // known x (side 1: middle rows)
+      const bool wr = jl < npiv && inx;
+      double* xw = a.x + (inx ? gl : 0);
+      const double* rp = buf + 31 * LSP + 32 + (31 - lane);             // &stage[jj][32 + jj - lane], jj = 31
+      const int step = LSP + 1;
+      if (msv == 4) {
+#pragma unroll 8
+        for (int jj = 31; jj >= 0; --jj) {
+          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
+          if (lane == jj && wr) *xw = xj;
+          rp -= step;
+        }
+      } else {
+#pragma unroll 4
+        for (int jj = 31; jj >= 0; --jj) {
+          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
+#pragma unroll
+          for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
+          if (lane == jj && wr) *xw = xj;
+          rp -= step;
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = (m == ms - 1) ? fresh : ((m + 1 < BC_MAXSLOT) ? yy[m + 1] : 0.0);
+      if (c == cpost) __threadfence();
+    }
+    __syncthreads();
+    if (c == cpost && tid == 0) bc_post(a.sync + 1, a.epoch);
+  }
+  if (a.prof && tid == 0 && side == 0) {
+    const long long tk3 = clock64();
+    a.prof[0] = tk1 - tk0; a.prof[1] = tk2 - tk1; a.prof[2] = tk3 - tk2; a.prof[3] = nsteps;
+  }
+}
+
 // Roles: workers (one BS x BS block of window slots each), helper lanes (one element each:
 // stream entry e of the upcoming rows into the ring with cp.async, 4 pivots ahead, and write
 // entry e of the finished column to global memory).
@@ -227,6 +378,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
   extern __shared__ __align__(16) double bc_smem[];
   __shared__ int s_fail;
   __shared__ double s_xI[4];
+  __shared__ double s_c4[16];
   constexpr int UN = 8;                     // pivots per unrolled body: ring slot and colbuf parity are compile-time
   const int side = blockIdx.x;
   // this side's pointers in registers (indexing the parameter block with blockIdx.x would turn every use into a
@@ -471,133 +623,458 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
     __syncthreads();
     if (tid == 0) bc_post(a.sync, a.epoch);
   }
-  // 1 / sqrt(d): normalisation of the stored columns, applied while staging the back substitution
-  for (int j = tid; j < npiv; j += blockDim.x) sd.dinv[j] = rsqrt(__ldcg(sd.dinv + j));
-  // ---- arrow corner: 3 x 3 intrinsics block and its right-hand side (thread of block {Wb, Wb})
-  if (side == 0 && tid == NT - 1) {
-    bool cbad = false;
-    const double m00 = v[0][0], m10 = v[1][0], m20 = v[2][0], m11 = v[1][1], m21 = v[2][1], m22 = v[2][2];
-    cbad |= !(m00 > 0.0);
-    const double l00 = sqrt(m00), l10 = m10 / l00, l20 = m20 / l00;
-    double t = m11 - l10 * l10;
-    cbad |= !(t > 0.0);
-    const double l11 = sqrt(t), l21 = (m21 - l20 * l10) / l11;
-    t = m22 - l20 * l20 - l21 * l21;
-    cbad |= !(t > 0.0);
-    const double l22 = sqrt(t);
-    const double z0 = v[3][0] / l00, z1 = (v[3][1] - l10 * z0) / l11, z2 = (v[3][2] - l20 * z0 - l21 * z1) / l22;
-    const double x2 = z2 / l22, x1 = (z1 - l21 * x2) / l11, x0 = (z0 - l10 * x1 - l20 * x2) / l00;
-    s_xI[0] = x0; s_xI[1] = x1; s_xI[2] = x2;
-    if (cbad || !isfinite(x0 + x1 + x2)) s_fail = 1;
+  if (worker && tid == NT - 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_c4[4 * i + k] = v[i][k];
   }
   __syncthreads();
-  if (tid == 0 && s_fail) atomicOr(a.fail, 1);
-  if (side == 0) {
-    if (s_fail) {
-      if (a.two && tid == 0) bc_post(a.sync + 1, a.epoch);     // side 1 must not wait for ever
-      return;
-    }
-    for (int s = a.nbg + tid; s < a.ns; s += blockDim.x) a.x[s] = (s < a.nbg + 3) ? s_xI[s - a.nbg] : 0.0;
-  } else {
-    // the middle x and the intrinsics come from side 0
-    if (tid == 0) {
-      bc_wait(a.sync + 1, a.epoch);
-      for (int k = 0; k < 3; ++k) s_xI[k] = __ldcg(a.x + a.nbg + k);
-    }
-    __syncthreads();
-  }
+  bc_tail<1>(a, sd, side, stage, s_fail, s_xI, s_c4, tk0, tk1);
+}
 
-  // ---- back substitution L' x = y - La' x_I in axpy form (warp 0; the other warps stage).
-  //      Lane l holds the running right-hand side of positions 32 (c - m) + l, m = 0 .. msv-1, of the
-  //      current 32-column chunk c.  stage[jj][32 + k] = -L[r][r - k] for 1 <= k <= bw (r = 32 c + jj),
-  //      zero elsewhere, so the inner step is one shared load and one fma per slot — no predicates;
-  //      per pivot one fma, one shuffle and one fma are on the dependent chain.  Rows >= npiv (side 1:
-  //      the middle rows) are not solved for: their x is known and only propagated.
-  const int ms = 1 + (bw + 31) / 32;
-  const int msv = ms <= 4 ? 4 : BC_MAXSLOT;
-  const int LSP = 32 * (msv + 1);
-  const int ctop = (nb + 31) / 32 - 1;
-  const int cpost = (a.two && side == 0) ? a.k0 / 32 : -1;     // after this chunk every middle x is written
-  const int CH = 32 * LSP;
-  // one row per warp and pass; all loads of a row (<= 7 x 2 per lane) are issued before the first use — with a
-  // dependent load pair per element the staging, not the substitution chain, set the pace (measured: 7.5 k cycles
-  // per 32-row chunk against 1.3 k for the chain)
-  auto stage_chunk = [&](int c, double* buf, int w0, int nw) {
-    for (int jj = w0; jj < 32; jj += nw) {
-      const int r = 32 * c + jj;
-      double lv[BC_MAXSLOT], dv[BC_MAXSLOT];
-#pragma unroll
-      for (int t = 0; t < BC_MAXSLOT; ++t) {
-        const int k = lane + 32 * t;                       // element q = 32 (t + 1) + lane of the padded row
-        const bool ok = t < msv && k >= 1 && k <= bw && r < nb && r - k >= 0 && r - k < npiv;
-        lv[t] = ok ? __ldcg(sd.Lr + (size_t)r * LS + k) : 0.0;
-        dv[t] = ok ? __ldcg(sd.dinv + r - k) : 0.0;
-      }
-      buf[jj * LSP + lane] = 0.0;
-#pragma unroll
-      for (int t = 0; t < BC_MAXSLOT; ++t)
-        if (t < msv) buf[jj * LSP + 32 * (t + 1) + lane] = -lv[t] * dv[t];
+// ------------------------------------------------------------------ block-6 form with look-ahead (k_band_chol6)
+//
+// The rank-1 kernel above pays ~450 cycles per pivot: ~65 instructions per lone worker warp and one CTA barrier
+// for 16 FMAs per thread.  The reduced camera system is made of 6 x 6 image blocks, so the natural unit is a
+// BLOCK pivot: per step k one 6 x 6 diagonal block is factored, the 6-column panel below it solved and the
+// trailing window updated with a rank-6 product — one barrier per six pivots, and the two dependent chains
+// (factor + solve of the next panel | rank-6 update of the window) run side by side in different warps:
+//   workers   one thread per unordered pair {P, Q} of ring POSITIONS (block index I lives at position I mod Wb,
+//             position Wb = the arrow rows), the 6 x 6 block T{P,Q}[a][b] = S[6 I_P + a][6 I_Q + b] in registers.
+//             Step k (pivot position c): every block that touches neither c nor cn = c + 1 takes the rank-6 update
+//             with panel k (shared memory); blocks touching c are dead (their content was panel k) and reload the
+//             incoming block row k + Wb straight from global memory — a full step ahead of their next use;
+//             blocks touching cn are dormant: the panel group carries that column.  At the end of the step the
+//             blocks touching cn2 = c + 2 (updated through pivot k) are published for the panel group.
+//   panel     one thread per row (position, a) of the next pivot column: takes the published row (or, for a freshly
+//             recycled position, the raw row it prefetched from global memory), applies update k itself (its own
+//             row of L_k is still in its registers), the 6 rows of the diagonal block are shared, EVERY panel
+//             thread factors the 6 x 6 block redundantly (LDL' recurrence: reciprocal, not square root, on the
+//             chain) and solves its own row on the fly; the normalised row goes to shared memory for the next
+//             step, the unnormalised one to global memory in the layout bc_tail expects.
+// One barrier of the 6 - 8 participating warps per step (bar.sync 1), one among the 3 - 5 panel warps (bar.sync 2);
+// the remaining warps of the CTA only exist for the back substitution's staging and sleep at the final barrier.
+// Phases end with a FLUSH step (no next panel: the workers update the dormant blocks too), after which the whole
+// window is current: that is where the two-sided form hands over and where a phase restarts.
+// Dataflow emulated block-wise against numpy before it was written; tests/test_gpu_band_chol.py.
+constexpr int B6_PBS = 38;        // doubles per 6 x 6 panel block in shared memory (304 bytes: the blocks of eight
+                                  // consecutive positions start in eight different groups of four banks)
+
+__device__ __forceinline__ void bc_gbar(int n) { asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bc_pbar(int n) { asm volatile("bar.sync 2, %0;\n" ::"r"(n) : "memory"); }
+
+template <int MAXT, int TR, int TC>
+__global__ void __launch_bounds__(MAXT, 1) k_band_chol6(const BandCholArgs a) {
+  // TR x TC: tile of a worker thread inside a 6 x 6 block (6 x 6: one thread per block; 3 x 6: two; 3 x 3: four).  Measured on B200
+  // (PSFM_CHOL_PROFILE): a warp executes ~1 instruction per 4.6 cycles whatever the dependences, so a step costs
+  // what its LONGEST warp executes — many thin threads beat few fat ones as long as the CTA has room for them.
+  extern __shared__ __align__(16) double bc_smem[];
+  __shared__ int s_fail;
+  __shared__ double s_xI[4];
+  __shared__ double s_c4[16];
+  constexpr int TPB = (6 / TR) * (6 / TC);
+  const int side = blockIdx.x;
+  BandSide sd;
+  sd.Ab = side ? a.s[1].Ab : a.s[0].Ab; sd.C4 = side ? a.s[1].C4 : a.s[0].C4;
+  sd.nb = side ? a.s[1].nb : a.s[0].nb; sd.npiv = side ? a.s[1].npiv : a.s[0].npiv;
+  sd.Lr = side ? a.s[1].Lr : a.s[0].Lr; sd.La = side ? a.s[1].La : a.s[0].La; sd.dinv = side ? a.s[1].dinv : a.s[0].dinv;
+  const int W = a.W, Wb = W / 6, RS = a.RS, nb = sd.nb, LS = a.bw + 1;
+  const int nsteps = sd.npiv / 6;
+  const int jsw = (a.two && side == 0) ? a.k0 / 6 : -1;
+  const int tid = threadIdx.x;
+  const int nblk = (Wb + 1) * (Wb + 2) / 2;
+  const int NWT = nblk * TPB;                   // worker threads
+  const int NW = (NWT + 31) & ~31;
+  const int NPR = 6 * (Wb + 1), NP = (NPR + 31) & ~31;
+  const int NG = NW + NP;
+  const int NG2 = (int)blockDim.x;       // the step barrier includes the loader warps (all remaining warps of the CTA)
+  const int PB = (Wb + 1) * B6_PBS;
+  // panel of step k in buffer k & 1, UNNORMALISED: Y = rows of the reduced pivot column (y), Z = y / d — the update is
+  // T -= Z_P Y_Q', no square root anywhere in the loop (bc_tail normalises what goes to the back substitution)
+  double* Ypan = bc_smem;               // [2][PB]
+  double* Zpan = Ypan + 2 * PB;         // [2][PB]
+  double* Raw = Zpan + 2 * PB;          // [2][PB] rows of the next pivot column, published at the end of step k in buffer k & 1
+  double* Raw0 = Raw + 2 * PB;          // [PB]    rows of the pivot column a phase starts with
+  double* Dsh = Raw0 + PB;              // [36]    diagonal block being factored
+  double* ring = Dsh + 36;              // [4][6 RS] incoming block rows: slot k & 3 holds block row k + Wb (raw rows of Ab) during step k
+  const int RB = 6 * RS;
+  const double* __restrict__ Ab = sd.Ab;
+  if (tid == 0) s_fail = 0;
+  const long long tk0 = a.prof ? clock64() : 0;
+  bool bad = false;
+  const int kb0 = 0, ke0 = jsw >= 0 ? jsw : nsteps;     // phase 0; phase 1 (two-sided, side 0): jsw .. nsteps
+
+  if (tid < NW) {
+    // ------------------------------------------------------------ workers
+    const bool act = tid < NWT;
+    const int blk = tid / TPB, sub = tid % TPB;
+    const int sr = TR * (sub / (6 / TC)), sc = TC * (sub % (6 / TC));   // tile origin inside the 6 x 6 block
+    int P = 0, Q = 0;
+    if (act) {
+      P = (int)((sqrtf(8.f * (float)blk + 1.f) - 1.f) * 0.5f);
+      while ((P + 1) * (P + 2) / 2 <= blk) ++P;
+      while (P * (P + 1) / 2 > blk) --P;
+      Q = blk - P * (P + 1) / 2;
     }
-  };
-  const double xi0 = s_xI[0], xi1 = s_xI[1], xi2 = s_xI[2];
-  auto y0 = [&](int i) -> double {
-    if (i < 0 || i >= npiv) return 0.0;
-    return __ldcg(sd.dinv + i) * (__ldcg(sd.La + 3 * (size_t)nb + i) -
-           (xi0 * __ldcg(sd.La + i) + xi1 * __ldcg(sd.La + (size_t)nb + i) + xi2 * __ldcg(sd.La + 2 * (size_t)nb + i)));
-  };
-  const int wid = tid >> 5, nwarp = blockDim.x >> 5;
-  stage_chunk(ctop, stage, wid, nwarp);
-  double yy[BC_MAXSLOT];
+    double T[TR][TC];
 #pragma unroll
-  for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = (tid < 32 && m < ms) ? y0(32 * (ctop - m) + lane) : 0.0;
-  __syncthreads();
-  const long long tk2 = a.prof ? clock64() : 0;
-  for (int c = ctop, n = 0; c >= 0; --c, ++n) {
-    const double* buf = stage + (n & 1) * CH;
-    if (tid >= 32) {
-      if (c > 0) stage_chunk(c - 1, stage + ((n + 1) & 1) * CH, wid - 1, nwarp - 1);
-    } else {
-      const double fresh = (c > 0) ? y0(32 * (c - ms) + lane) : 0.0;     // slot ms - 1 of the next chunk
-      const int jl = 32 * c + lane;
-      const double dl = (jl < npiv) ? __ldcg(sd.dinv + jl) : 0.0;
-      // global index of local row jl: side 0 jl, side 1 nbp - 1 - jl; rows past nbg are identity padding (x = 0)
-      const int gl = side ? a.nbp - 1 - jl : jl;
-      const bool inx = jl < nb && gl >= 0 && gl < a.nbg;
-      const double xk = (jl >= npiv && inx) ? __ldcg(a.x + gl) : 0.0;   // known x (side 1: middle rows)
-      const bool wr = jl < npiv && inx;
-      double* xw = a.x + (inx ? gl : 0);
-      const double* rp = buf + 31 * LSP + 32 + (31 - lane);             // &stage[jj][32 + jj - lane], jj = 31
-      const int step = LSP + 1;
-      if (msv == 4) {
-#pragma unroll 8
-        for (int jj = 31; jj >= 0; --jj) {
-          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
+    for (int i = 0; i < TR; ++i)
 #pragma unroll
-          for (int m = 0; m < 4; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
-          if (lane == jj && wr) *xw = xj;
-          rp -= step;
+      for (int k = 0; k < TC; ++k) {
+        double x = 0.0;
+        const int bi = sr + i, bk = sc + k;
+        if (act) {
+          if (P < Wb) {
+            const int r = 6 * P + bi, c = 6 * Q + bk, hi = max(r, c), lo = min(r, c);
+            x = __ldg(Ab + (size_t)hi * RS + (hi - lo));
+          } else if (Q < Wb) { if (bi < 4) x = __ldg(Ab + (size_t)(6 * Q + bk) * RS + W + bi); }
+          else if (bi < 4 && bk < 4) x = __ldg(sd.C4 + 4 * bi + bk);
         }
+        T[i][k] = x;
+      }
+    // rows of pivot column `pos` held by this tile -> dst[row position][a][0..5]
+    auto publish = [&](double* dst, int pos) {
+      if (Q == pos) {
+        double* o = dst + P * B6_PBS + 6 * sr + sc;
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int k = 0; k < TC; ++k) o[6 * i + k] = T[i][k];
+      } else if (P == pos) {
+        double* o = dst + Q * B6_PBS + 6 * sc + sr;
+#pragma unroll
+        for (int k = 0; k < TC; ++k)
+#pragma unroll
+          for (int i = 0; i < TR; ++i) o[6 * k + i] = T[i][k];
+      }
+    };
+    // T -= Z_P Y_Q' with the panel in shared memory (rows of 6 doubles, 16-byte aligned)
+    auto update = [&](const double* Yb, const double* Zb) {
+      const double2* lq = reinterpret_cast<const double2*>(Yb + Q * B6_PBS + 6 * sc);
+      const double2* lp = reinterpret_cast<const double2*>(Zb + P * B6_PBS + 6 * sr);
+      double q[TC][6];
+#pragma unroll
+      for (int k = 0; k < TC; ++k)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const double2 z = lq[3 * k + m]; q[k][2 * m] = z.x; q[k][2 * m + 1] = z.y; }
+#pragma unroll
+      for (int i = 0; i < TR; ++i) {
+        double pr[6];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const double2 z = lp[3 * i + m]; pr[2 * m] = z.x; pr[2 * m + 1] = z.y; }
+#pragma unroll
+        for (int k = 0; k < TC; ++k)
+#pragma unroll
+          for (int m = 0; m < 6; ++m) T[i][k] = fma(-pr[m], q[k][m], T[i][k]);
+      }
+    };
+    // position c takes block row k + Wb (raw entries: no pivot <= k reaches it), staged in ring slot k & 3 by the
+    // loader warp; cn = (k + 1) mod Wb holds block k + 1
+    auto recycle = [&](int k, int c, int cn) {
+      const int rn = 6 * (k + Wb);
+      const double* rg = ring + (k & 3) * RB;            // rg[i * RS + e] = A[rn + i][rn + i - e]
+      if (P == c && Q == c) {
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int kk = 0; kk < TC; ++kk) {
+            const int bi = sr + i, bk = sc + kk;
+            T[i][kk] = rg[max(bi, bk) * RS + (bi > bk ? bi - bk : bk - bi)];
+          }
+      } else if (P == Wb) {
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int kk = 0; kk < TC; ++kk) T[i][kk] = (sr + i < 4) ? rg[(sc + kk) * RS + W + sr + i] : 0.0;
       } else {
-#pragma unroll 4
-        for (int jj = 31; jj >= 0; --jj) {
-          const double xj = __shfl_sync(0xffffffffu, fma(yy[0], dl, xk), jj);
+        const int o = (P == c) ? Q : P;
+        int dI = o - cn; if (dI < 0) dI += Wb;
+        const int ro = 6 * (k + 1 + dI);
+        if (P == c) {
 #pragma unroll
-          for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = fma(rp[32 * m], xj, yy[m]);
-          if (lane == jj && wr) *xw = xj;
-          rp -= step;
+          for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int kk = 0; kk < TC; ++kk) T[i][kk] = rg[(sr + i) * RS + (rn + sr + i - ro - sc - kk)];
+        } else {
+#pragma unroll
+          for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int kk = 0; kk < TC; ++kk) T[i][kk] = rg[(sc + kk) * RS + (rn + sc + kk - ro - sr - i)];
         }
       }
+    };
+    // column block k of the factor (panel k, unnormalised) -> global memory in the layout bc_tail reads; one
+    // element per worker thread and pass (the workers have slack: the panel group is the longer chain)
+    auto output = [&](int k, int c) {
+      const double* Yb = Ypan + (k & 1) * PB;
+      const int jb = 6 * k;
+      for (int v = tid; v < 36 * (Wb + 1); v += NW) {
+        const int p = v / 36, e = v - 36 * p, ar = e / 6, m = e - 6 * ar;
+        const double y = Yb[p * B6_PBS + e];
+        if (p == c) {
+          if (m <= ar) sd.Lr[(size_t)(jb + ar) * LS + (ar - m)] = y;
+          if (m == ar) sd.dinv[jb + ar] = y;
+        } else if (p < Wb) {
+          int dI = p - c; if (dI < 0) dI += Wb;
+          const int rr = 6 * (k + dI) + ar, kk = rr - jb - m;
+          if (rr < nb && kk < LS) sd.Lr[(size_t)rr * LS + kk] = y;          // beyond bw: structurally zero
+        } else if (ar < 4) {
+          sd.La[(size_t)ar * nb + jb + m] = y;
+        }
+      }
+    };
+    long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0, q_upd = 0, q_rec = 0, q_pub = 0;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      const int kb = phase == 0 ? kb0 : jsw, ke = phase == 0 ? ke0 : nsteps;
+      if (phase == 1) {
+        if (jsw < 0) break;
+        // two-sided form: the window is current through pivot k0 - 1; add side 1's update of the same rows
+        if (tid == 0) bc_wait(a.sync, a.epoch);
+        bc_gbar(NG2);
+        if (act) {
+          const int cb = jsw % Wb;
+          const double* DA = a.D + (size_t)W * W;
+          int dP = P - cb; if (dP < 0) dP += Wb;
+          int dQ = Q - cb; if (dQ < 0) dQ += Wb;
 #pragma unroll
-      for (int m = 0; m < BC_MAXSLOT; ++m) yy[m] = (m == ms - 1) ? fresh : ((m + 1 < BC_MAXSLOT) ? yy[m + 1] : 0.0);
-      if (c == cpost) __threadfence();
+          for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int k = 0; k < TC; ++k) {
+              const int bi = sr + i, bk = sc + k;
+              if (P < Wb) T[i][k] += __ldcg(a.D + (size_t)(6 * dP + bi) * W + 6 * dQ + bk);
+              else if (Q < Wb) { if (bi < 4) T[i][k] += __ldcg(DA + (size_t)bi * W + 6 * dQ + bk); }
+              else if (bi < 4 && bk < 4) T[i][k] += __ldcg(DA + 4 * (size_t)W + 4 * bi + bk);
+            }
+        }
+      }
+      // (re)start: the whole window is current; hand the pivot column and the next one to the panel group
+      int c = kb % Wb;
+      {
+        const int cn = c + 1 == Wb ? 0 : c + 1;
+        if (act) {
+          publish(Raw0, c);
+          if (P != c && Q != c) publish(Raw + ((kb - 1) & 1) * PB, cn);
+        }
+        bc_gbar(NG2);
+        bc_gbar(NG2);
+      }
+#pragma unroll 1
+      for (int k = kb; k < ke; ++k) {
+        const bool last = k == ke - 1;
+        const int cn = c + 1 == Wb ? 0 : c + 1, cn2 = cn + 1 == Wb ? 0 : cn + 1;
+        if (act) {
+          const bool ic = (P == c || Q == c), icn = (P == cn || Q == cn);
+          long long t0 = a.prof ? clock64() : 0;
+          if (ic) { if (!icn || last) recycle(k, c, cn); }
+          else if (!icn || last) update(Ypan + (k & 1) * PB, Zpan + (k & 1) * PB);
+          if (a.prof) { const long long t1 = clock64(); if (ic) q_rec += t1 - t0; else q_upd += t1 - t0; t0 = t1; }
+          if (!last && !ic && !icn && (P == cn2 || Q == cn2)) publish(Raw + (k & 1) * PB, cn2);
+          if (a.prof) q_pub += clock64() - t0;
+        }
+        output(k, c);
+        if (a.prof) { const long long t = clock64(); p_own += t - tlast; tlast = t; }
+        bc_gbar(NG2);
+        if (a.prof) { const long long t = clock64(); p_wait += t - tlast; tlast = t; }
+        c = cn;
+      }
     }
-    __syncthreads();
-    if (c == cpost && tid == 0) bc_post(a.sync + 1, a.epoch);
+    if (a.prof && tid == 0 && side == 0) { a.prof[6] = p_own; a.prof[7] = p_wait; a.prof[8] = q_upd; a.prof[9] = q_rec; a.prof[10] = q_pub; }
+    if (act && a.two && side == 1) {
+      // hand-over: what is left in the window (rows n1 .. n1 + W - 1 of the reversed matrix, zero on input) is the
+      // update of the middle block by this side's pivots; reversed row n1 + m is middle row W - 1 - m
+      const int cb = nsteps % Wb;
+      double* DA = a.D + (size_t)W * W;
+      int dP = P - cb; if (dP < 0) dP += Wb;
+      int dQ = Q - cb; if (dQ < 0) dQ += Wb;
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int k = 0; k < TC; ++k) {
+          const int bi = sr + i, bk = sc + k;
+          const int mk = W - 1 - (6 * dQ + bk);
+          if (P < Wb) {
+            const int mi = W - 1 - (6 * dP + bi);
+            a.D[(size_t)mi * W + mk] = T[i][k];
+            if (P != Q) a.D[(size_t)mk * W + mi] = T[i][k];
+          } else if (Q < Wb) { if (bi < 4) DA[(size_t)bi * W + mk] = T[i][k]; }
+          else if (bi < 4 && bk < 4) DA[4 * (size_t)W + 4 * bi + bk] = T[i][k];
+        }
+    }
+    if (act && blk == nblk - 1) {
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int k = 0; k < TC; ++k)
+          if (sr + i < 4 && sc + k < 4) s_c4[4 * (sr + i) + sc + k] = T[i][k];
+    }
+  } else if (tid < NG) {
+    // ------------------------------------------------------------ panel group: thread = row (position p, a)
+    const int r = tid - NW;
+    const bool pact = r < NPR;
+    const int p = pact ? r / 6 : 0, ar = pact ? r % 6 : 0;
+    double yo[6] = {0, 0, 0, 0, 0, 0};     // own row of the current panel (unnormalised)
+    int kre = -1;                         // step at which this thread's position was recycled last (in this phase)
+    // raw row ar of block row kr + Wb (ring slot kr & 3) against column block j: A[r][6 j + m], r = 6 (kr + Wb) + ar
+    auto ring_row = [&](int kr, int j, double (&dst)[6]) {
+      const double* rg = ring + (kr & 3) * RB + ar * RS + (6 * (kr + Wb) + ar - 6 * j);
+#pragma unroll
+      for (int m = 0; m < 6; ++m) dst[m] = rg[-m];
+    };
+    long long p_own = 0, p_wait = 0, tlast = a.prof ? clock64() : 0, q_pbar = 0, q_chol = 0, q_out = 0;
+    // col = row (p, ar) of the fully updated pivot column block at position cp: factor the diagonal block (LDL'
+    // recurrence, every thread redundantly: one reciprocal per pivot on the chain), solve the row on the fly,
+    // publish y and z = y / d
+    auto finish = [&](int cp, double (&col)[6], double* Ydst, double* Zdst) {
+      if (pact && p == cp) {
+        double2* o = reinterpret_cast<double2*>(Dsh + 6 * ar);
+#pragma unroll
+        for (int m = 0; m < 6; m += 2) o[m >> 1] = make_double2(col[m], col[m + 1]);
+      }
+      long long tq = a.prof ? clock64() : 0;
+      bc_pbar(NP);
+      if (a.prof) { const long long t = clock64(); q_pbar += t - tq; tq = t; }
+      double Dl[6][6], w[6][6], invd[6];
+      {
+        double dfull[36];
+        const double2* dd = reinterpret_cast<const double2*>(Dsh);
+#pragma unroll
+        for (int t = 0; t < 18; ++t) { const double2 z = dd[t]; dfull[2 * t] = z.x; dfull[2 * t + 1] = z.y; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) Dl[i][j] = dfull[6 * i + j];
+      }
+      const bool diag = p == cp;
+      double z[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double dj = Dl[j][j];
+        bad |= !(dj > 0.0 && dj <= 1.7976931348623157e308);
+        invd[j] = bc_rcp(dj);
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) w[i][j] = Dl[i][j] * invd[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i)
+#pragma unroll
+          for (int i2 = j + 1; i2 <= i; ++i2) Dl[i][i2] = fma(-Dl[i][j], w[i2][j], Dl[i][i2]);
+        // row solve, column j: y_j = col_j - sum_{n < j} y_n w[j][n]
+        double t = col[j];
+#pragma unroll
+        for (int n = 0; n < j; ++n) t = fma(-yo[n], w[j][n], t);
+        if (diag && j > ar) t = 0.0;       // upper part of the diagonal block
+        yo[j] = t;
+        z[j] = t * invd[j];
+      }
+      if (a.prof) { const long long t = clock64(); q_chol += t - tq + (z[5] == 1.25e-300 ? 1 : 0); tq = t; }
+      if (pact) {
+        double2* oy = reinterpret_cast<double2*>(Ydst + p * B6_PBS + 6 * ar);
+        double2* oz = reinterpret_cast<double2*>(Zdst + p * B6_PBS + 6 * ar);
+#pragma unroll
+        for (int m = 0; m < 6; m += 2) { oy[m >> 1] = make_double2(yo[m], yo[m + 1]); oz[m >> 1] = make_double2(z[m], z[m + 1]); }
+      }
+      if (a.prof) q_out += clock64() - tq;
+    };
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      const int kb = phase == 0 ? kb0 : jsw, ke = phase == 0 ? ke0 : nsteps;
+      if (phase == 1) {
+        if (jsw < 0) break;
+        bc_gbar(NG2);
+      }
+      int c = kb % Wb;
+      kre = -1;
+      bc_gbar(NG2);
+      {
+        double col[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) col[m] = pact ? Raw0[p * B6_PBS + 6 * ar + m] : 0.0;
+        finish(c, col, Ypan + (kb & 1) * PB, Zpan + (kb & 1) * PB);
+      }
+      bc_gbar(NG2);
+#pragma unroll 1
+      for (int k = kb; k < ke; ++k) {
+        const bool last = k == ke - 1;
+        const int cn = c + 1 == Wb ? 0 : c + 1;
+        if (!last) {
+          double col[6];
+          const bool useA = pact && p == c && p < Wb;          // recycled in this step: row of block k + Wb, no update
+          if (useA) { ring_row(k, k + 1, col); kre = k; }
+          else if (pact && kre == k - 1 && kre >= 0) ring_row(k - 1, k + 1, col);   // recycled in the previous step
+          else {
+            const double2* rawp = reinterpret_cast<const double2*>(Raw + ((k - 1) & 1) * PB + p * B6_PBS + 6 * ar);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) { const double2 v = rawp[m]; col[2 * m] = pact ? v.x : 0.0; col[2 * m + 1] = pact ? v.y : 0.0; }
+          }
+          if (!useA) {
+            const double2* Zcn = reinterpret_cast<const double2*>(Zpan + (k & 1) * PB + cn * B6_PBS);
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+              double t = col[m];
+#pragma unroll
+              for (int n = 0; n < 3; ++n) { const double2 v = Zcn[3 * m + n]; t = fma(-yo[2 * n], v.x, t); t = fma(-yo[2 * n + 1], v.y, t); }
+              col[m] = t;
+            }
+          }
+          finish(cn, col, Ypan + ((k + 1) & 1) * PB, Zpan + ((k + 1) & 1) * PB);
+        }
+        if (a.prof) { const long long t = clock64(); p_own += t - tlast; tlast = t; }
+        bc_gbar(NG2);
+        if (a.prof) { const long long t = clock64(); p_wait += t - tlast; tlast = t; }
+        c = cn;
+      }
+    }
+    if (a.prof && tid == NW && side == 0) { a.prof[4] = p_own; a.prof[5] = p_wait; a.prof[11] = q_pbar; a.prof[12] = q_chol; a.prof[13] = q_out; }
+  } else {
+    // ------------------------------------------------------------ loader warps: block row k + Wb of Ab -> ring slot k & 3,
+    //      one step before it is used, loaded from global memory one step before that (registers in between)
+    const int lt = tid - NG, nl = (int)blockDim.x - NG;
+    const int maxblk = nsteps - 1 + Wb;                  // last block row anybody reads
+    constexpr int LPT = 12;                              // double2 per loader thread: 32 loaders x 12 x 2 = 768 >= 6 RS up to Wb = 20, 64 loaders for all
+    double2 rg[LPT];
+    auto ld = [&](int blk) {
+      const double2* src = reinterpret_cast<const double2*>(Ab + (size_t)6 * blk * RS);
+#pragma unroll
+      for (int u = 0; u < LPT; ++u) {
+        const int e = lt + u * nl;
+        rg[u] = (blk <= maxblk && 2 * e < RB) ? __ldg(src + e) : make_double2(0.0, 0.0);
+      }
+    };
+    auto st_ = [&](int slot) {
+      double2* dst = reinterpret_cast<double2*>(ring + slot * RB);
+#pragma unroll
+      for (int u = 0; u < LPT; ++u) {
+        const int e = lt + u * nl;
+        if (2 * e < RB) dst[e] = rg[u];
+      }
+    };
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      const int kb = phase == 0 ? kb0 : jsw, ke = phase == 0 ? ke0 : nsteps;
+      if (phase == 1) {
+        if (jsw < 0) break;
+        bc_gbar(NG2);
+      }
+      ld(kb + Wb); st_(kb & 3);
+      ld(kb + 1 + Wb);
+      bc_gbar(NG2);
+      bc_gbar(NG2);
+#pragma unroll 1
+      for (int k = kb; k < ke; ++k) {
+        st_((k + 1) & 3);
+        ld(k + 2 + Wb);
+        bc_gbar(NG2);
+      }
+    }
   }
-  if (a.prof && tid == 0 && side == 0) {
-    const long long tk3 = clock64();
-    a.prof[0] = tk1 - tk0; a.prof[1] = tk2 - tk1; a.prof[2] = tk3 - tk2; a.prof[3] = nsteps;
-  }
+  if (a.two && side == 1) __threadfence();
+  __syncthreads();
+  const long long tk1 = a.prof ? clock64() : 0;
+  if (bad) s_fail = 1;
+  if (a.two && side == 1 && tid == 0) bc_post(a.sync, a.epoch);
+  __syncthreads();
+  bc_tail<2>(a, sd, side, bc_smem, s_fail, s_xI, s_c4, tk0, tk1);
 }
 
 // threads of the kernel for window W with BS x BS blocks
@@ -622,12 +1099,35 @@ inline int band_chol_rows(int nb, int W) { return ((nb + 7) & ~7) + W + 8; }
 
 // How the pivot chain is cut.  Two-sided from 4 windows on (below that the hand-over costs more than
 // the shorter chain saves); PSFM_CHOL_ONE_SIDED forces the one-CTA form.
-inline BandPlan band_chol_plan(int nb, int bw) {
+// blk_span >= 0: the matrix is made of 6 x 6 blocks and blocks further apart than blk_span are zero (the reduced
+// camera system: blk_span = longest image span of a track); -1: only the scalar half bandwidth bw is known.
+inline BandPlan band_chol_plan(int nb, int bw, int blk_span = -1) {
   BandPlan p{};
   p.nb = nb; p.bw = std::min(bw, nb - 1);
+  static const bool one = getenv("PSFM_CHOL_ONE_SIDED") != nullptr;
+  static const bool rank1 = getenv("PSFM_CHOL_RANK1") != nullptr;
+  // window of the block-6 kernel, in blocks: every block at distance >= Wb from the pivot block must be zero
+  int Wb6 = blk_span >= 0 ? blk_span + 1 : (p.bw + 5) / 6 + 1;
+  if (nb % 6 == 0) Wb6 = std::max(3, std::min(Wb6, nb / 6));
+  if (!rank1 && nb % 6 == 0 && nb / 6 >= 3 && Wb6 <= 25 && 6 * Wb6 > p.bw) {
+    // block-6 form: W = 6 Wb, everything in units of image blocks
+    const int F = nb / 6, Wb = Wb6;
+    p.blk6 = 1;
+    p.W = 6 * Wb; p.RS = p.W + 4; p.nbp = nb;
+    p.two = (!one && F >= 4 * Wb) ? 1 : 0;
+    if (p.two) {
+      p.k0 = 6 * ((F - Wb) / 2);
+      p.n1 = p.nbp - p.W - p.k0;
+      p.nbs[0] = p.k0 + p.W; p.npiv[0] = p.k0 + p.W;
+      p.nbs[1] = p.n1 + p.W; p.npiv[1] = p.n1;
+      p.rows[0] = band_chol_rows(p.nbs[0], p.W); p.rows[1] = band_chol_rows(p.nbs[1], p.W);
+    } else {
+      p.nbs[0] = nb; p.npiv[0] = nb; p.rows[0] = band_chol_rows(nb, p.W);
+    }
+    return p;
+  }
   p.W = band_chol_window(p.bw); p.RS = p.W + 4;
   p.nbp = (nb + 7) & ~7;
-  static const bool one = getenv("PSFM_CHOL_ONE_SIDED") != nullptr;
   p.two = (p.W > 0 && !one && p.nbp >= 4 * p.W) ? 1 : 0;
   if (p.two) {
     p.k0 = (((p.nbp - p.W) / 2 + 7) / 8) * 8;
@@ -669,20 +1169,49 @@ struct BandWork {
       c.s[s].Lr = Lr.p + o * LS; c.s[s].La = La.p + 4 * o; c.s[s].dinv = dinv.p + o;
     }
     c.two = pl.two; c.nbg = pl.nb; c.nbp = pl.nbp; c.k0 = pl.k0;
-    c.bw = pl.bw; c.W = pl.W; c.RS = pl.RS; c.ns = ns;
+    c.bw = pl.bw; c.W = pl.W; c.RS = pl.RS; c.ns = ns; c.blk6 = pl.blk6;
     c.x = x; c.fail = fail; c.D = D.p; c.sync = sync.p; c.epoch = ++epoch;
     c.prof = nullptr;
     return c;
   }
 };
 
-// one launch (4 x 4 register blocks): one CTA, or two for the two-sided form
+// one launch: one CTA, or two for the two-sided form
 inline void band_chol_launch(BandCholArgs c, cudaStream_t st) {
   static const int flags = getenv("PSFM_CHOL_FLAGS") ? atoi(getenv("PSFM_CHOL_FLAGS")) : 0;
   c.flags = flags;
+  const int grid = c.two ? 2 : 1;
+  if (c.blk6) {
+    const int Wb = c.W / 6, nblk = (Wb + 1) * (Wb + 2) / 2;
+    const int np = (6 * (Wb + 1) + 31) & ~31;
+    const int ng4 = ((4 * nblk + 31) & ~31) + np, ng1 = ((nblk + 31) & ~31) + np;
+    const size_t fact = sizeof(double) * (7 * (size_t)(Wb + 1) * B6_PBS + 36 + 4 * 6 * (size_t)c.RS);
+    const size_t smem = std::max(fact, band_chol_smem(c.bw));
+    static const bool fat = getenv("PSFM_CHOL_FAT") != nullptr;     // measurement: one thread per block everywhere
+#define PSFM_BC6_GO(MT, TRV, TCV)                                                                                      \
+  do {                                                                                                             \
+    static size_t attr = 0;                                                                                        \
+    if (smem > attr) {                                                                                             \
+      PSFM_CUDA(cudaFuncSetAttribute(k_band_chol6<MT, TRV, TCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr = smem;                                                                                                 \
+    }                                                                                                              \
+    k_band_chol6<MT, TRV, TCV><<<grid, MT, smem, st>>>(c);                                                               \
+  } while (0)
+    // thin threads while the CTA has room for them (measured, profiles/r02_band_chol_notes.md), else one fat thread
+    // per block; the threads after the workers and the panel group are the loader (>= 32)
+    static const int tile = getenv("PSFM_CHOL_TILE") ? atoi(getenv("PSFM_CHOL_TILE")) : 0;     // measurement: 33 | 36 | 66
+    const int ng2 = ((2 * nblk + 31) & ~31) + np;
+    if (!fat && tile != 36 && tile != 66 && ng4 + 32 <= 512) PSFM_BC6_GO(512, 3, 3);
+    else if (!fat && tile != 66 && ng2 + 32 <= 384) PSFM_BC6_GO(384, 3, 6);
+    else if (ng1 + 64 <= 256) PSFM_BC6_GO(256, 6, 6);
+    else if (ng1 + 64 <= 512) PSFM_BC6_GO(512, 6, 6);
+    else PSFM_BC6_GO(640, 6, 6);
+#undef PSFM_BC6_GO
+    PSFM_LAUNCH_CHECK();
+    return;
+  }
   const int threads = band_chol_threads(c.W, 4);
   const size_t smem = band_chol_smem(c.bw);
-  const int grid = c.two ? 2 : 1;
 #define PSFM_BC_GO(BSV, MT)                                                                                        \
   do {                                                                                                             \
     static size_t attr = 0;                                                                                        \

@@ -60,7 +60,7 @@ struct TileCtx {
 };
 
 struct Lin {        // stored linearisation, SoA by component, index k*M + i
-  double* r;        // [2][M] loss-corrected residuals
+  double* r;        // [M][2] loss-corrected residuals (interleaved: one 16-byte access per observation)
   double* a;        // [3][M] a00, a02, a12
 };
 
@@ -91,40 +91,56 @@ __device__ __forceinline__ void loss_eval(const LossP l, const double s, double&
 
 // ------------------------------------------------------------------ tile plumbing
 
-// Shared memory of a tile kernel (all SoA so that lanes of one point / one image broadcast):
+// Shared memory of a tile kernel:
 //   sv   [NV][TILE + 1]  per-observation values being reduced (row stride PSFM_SVS)
 //   sw   [4][cap_np]     per-point scratch
 //   sred [9*32]          block-reduction scratch
-//   simg [12][cap_ns]    per image segment: R (row-major 9), t (3)
+//   simg [cap_ns][14]    per image segment, AoS: R (row-major 9), t (3), pad (2) — 112 bytes: 16-byte aligned rows
+//                        (one bulk copy per tile from seg_pose) and eight consecutive segments start in eight
+//                        different groups of four banks
 //   sx   [6][cap_ns]     per image segment: scaled input vector (rot 3 | t 3)
-//   spt  [NPT][cap_np]   per point: X (3) [, H~ (6) [, w^ or G'E focal row (3) [, w^ (3)]]]
+//   sxyz [cap_np][3]     per point, AoS: X
+//   spt  rows 3..NPT-1   per point, SoA rows of stride pstr: H~ (rows 3-8), w^ or G'E focal row (9-11), w^ (12-14);
+//                        row r starts at spt + r * pstr + lead, where lead (0 | 1 doubles) is what the 16-byte
+//                        alignment of the bulk copy of that row left in front (0 in the non-pipelined kernels)
 // Row stride of sv: TILE + 1 so that lanes working on different components k of the same
 // observation column hit different banks (the reductions below run component-fastest).
 #define PSFM_SVS (TILE + 1)
+constexpr int PSFM_SPS = 14;      // doubles per segment pose record
 
 template <int TILE>
 struct TileSmem {
-  double *sv, *sw, *sred, *simg, *sx, *spt;
+  double *sv, *sw, *sred, *simg, *sx, *spt, *sxyz;
   int *pstart, *coff, *cimg;
   unsigned short* perm;
   int cap_ns, cap_np;
+  int pstr, plead0, plead1;    // spt row stride; lead of the rows that are EVEN / ODD rows of their global SoA array
   static size_t bytes(int nv, int npt, int cap_ns, int cap_np) {
-    return sizeof(double) * ((size_t)nv * PSFM_SVS + 4 * (size_t)cap_np + 9 * 32 + 18 * (size_t)cap_ns + (size_t)npt * cap_np) +
+    return sizeof(double) * ((size_t)nv * PSFM_SVS + 4 * (size_t)cap_np + 9 * 32 + (PSFM_SPS + 6) * (size_t)cap_ns + (size_t)npt * cap_np +
+                             3 * (size_t)cap_np + 2) +
            sizeof(int) * ((size_t)cap_np + 2 * (size_t)cap_ns + 4) + sizeof(unsigned short) * (size_t)TILE + 32;
   }
   __device__ __forceinline__ void carve(unsigned char* base, int nv, int npt, int cns, int cnp) {
     cap_ns = cns; cap_np = cnp;
+    pstr = cnp; plead0 = 0; plead1 = 0;
     sv = reinterpret_cast<double*>(base);
     sw = sv + (size_t)nv * PSFM_SVS;
     sred = sw + 4 * (size_t)cnp;
     simg = sred + 9 * 32;
-    sx = simg + 12 * (size_t)cns;
+    sx = simg + PSFM_SPS * (size_t)cns;
     spt = sx + 6 * (size_t)cns;
-    pstart = reinterpret_cast<int*>(spt + (size_t)npt * cnp);
+    sxyz = spt + (size_t)npt * cnp;
+    pstart = reinterpret_cast<int*>(sxyz + 3 * (size_t)cnp + 2);
     coff = pstart + cnp + 1;
     cimg = coff + cns + 1;
     perm = reinterpret_cast<unsigned short*>(cimg + cns + 1);
   }
+  // row r (3 .. 14) of the per-point SoA block: rows 3-8 are rows 0-5 of their global array, 9-11 and 12-14 rows 0-2
+  __device__ __forceinline__ const double* prow(int r) const {
+    const int kpar = (r < 12) ? ((r + 1) & 1) : (r & 1);
+    return spt + (size_t)r * pstr + (kpar ? plead1 : plead0);
+  }
+  __device__ __forceinline__ double* prow_w(int r) const { return const_cast<double*>(prow(r)); }
 };
 
 struct TileInfo {
@@ -168,7 +184,7 @@ __device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE>
   for (int j = tid; j < ti.ns * 12; j += TILE) {
     const int s = j / 12, k = j - 12 * s;
     const int img = __ldg(tc.cseg_img + ti.cs0 + s);
-    sm.simg[k * cns + s] = __ldg(pose16 + 16 * (size_t)img + k);
+    sm.simg[s * PSFM_SPS + k] = __ldg(pose16 + 16 * (size_t)img + k);
   }
   if (xs) {
     for (int j = tid; j < ti.ns * 6; j += TILE) {
@@ -177,26 +193,23 @@ __device__ __forceinline__ void tile_fill_smem(const TileCtx& tc, TileSmem<TILE>
       sm.sx[k * cns + s] = __ldg(xs + 6 * (size_t)img + k);
     }
   }
-  for (int j = tid; j < ti.np * 3; j += TILE) {
-    const int l = j / 3, k = j - 3 * l;
-    sm.spt[k * cnp + l] = __ldg(X + 3 * (size_t)ti.pt0 + j);
-  }
+  for (int j = tid; j < ti.np * 3; j += TILE) sm.sxyz[j] = __ldg(X + 3 * (size_t)ti.pt0 + j);
   if (p6) {
     for (int j = tid; j < ti.np * 6; j += TILE) {
       const int k = j / ti.np, l = j - k * ti.np;
-      sm.spt[(3 + k) * cnp + l] = __ldg(p6 + (size_t)k * tc.P + ti.pt0 + l);
+      sm.prow_w(3 + k)[l] = __ldg(p6 + (size_t)k * tc.P + ti.pt0 + l);
     }
   }
   if (p3) {
     for (int j = tid; j < ti.np * 3; j += TILE) {
       const int k = j / ti.np, l = j - k * ti.np;
-      sm.spt[(9 + k) * cnp + l] = __ldg(p3 + (size_t)k * tc.P + ti.pt0 + l);
+      sm.prow_w(9 + k)[l] = __ldg(p3 + (size_t)k * tc.P + ti.pt0 + l);
     }
   }
   if (p3b) {
     for (int j = tid; j < ti.np * 3; j += TILE) {
       const int k = j / ti.np, l = j - k * ti.np;
-      sm.spt[(12 + k) * cnp + l] = __ldg(p3b + (size_t)k * tc.P + ti.pt0 + l);
+      sm.prow_w(12 + k)[l] = __ldg(p3b + (size_t)k * tc.P + ti.pt0 + l);
     }
   }
   __syncthreads();
@@ -271,9 +284,9 @@ template <int TILE>
 __device__ __forceinline__ void load_geom(const TileSmem<TILE>& sm, int ls, int lp, ObsGeom& g) {
   const int cns = sm.cap_ns, cnp = sm.cap_np;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) g.R[k] = sm.simg[k * cns + ls];
-  g.tz = sm.simg[11 * cns + ls];
-  const double X0 = sm.spt[lp], X1 = sm.spt[cnp + lp], X2 = sm.spt[2 * cnp + lp];
+  for (int k = 0; k < 9; ++k) g.R[k] = sm.simg[ls * PSFM_SPS + k];
+  g.tz = sm.simg[ls * PSFM_SPS + 11];
+  const double X0 = sm.sxyz[3 * lp], X1 = sm.sxyz[3 * lp + 1], X2 = sm.sxyz[3 * lp + 2];
 #pragma unroll
   for (int a = 0; a < 3; ++a) g.w[a] = g.R[3 * a] * X0 + g.R[3 * a + 1] * X1 + g.R[3 * a + 2] * X2;
 }
@@ -343,7 +356,7 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
   if (act) {
     load_geom<TILE>(sm, ls, lp, g);
     const int cns = sm.cap_ns;
-    const double p0 = g.w[0] + sm.simg[9 * cns + ls], p1 = g.w[1] + sm.simg[10 * cns + ls], p2 = g.w[2] + g.tz;
+    const double p0 = g.w[0] + sm.simg[ls * PSFM_SPS + 9], p1 = g.w[1] + sm.simg[ls * PSFM_SPS + 10], p2 = g.w[2] + g.tz;
     const double iz = 1.0 / p2;
     const double u = p0 * iz, v = p1 * iz;
     const int cam = __ldg(tc.img_cam + sm.cimg[ls]);
@@ -358,8 +371,7 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
     a00 = sq * f * iz;
     a02 = -a00 * u;
     a12 = -a00 * v;
-    a.L.r[i] = r0;
-    a.L.r[M + i] = r1;
+    reinterpret_cast<double2*>(a.L.r)[i] = make_double2(r0, r1);
     a.L.a[i] = a00;
     a.L.a[M + i] = a02;
     a.L.a[2 * M + i] = a12;
@@ -618,9 +630,9 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_prep(cons
     const int cnp = sm.cap_np;
     double hv[6], w[3];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+    for (int k = 0; k < 6; ++k) hv[k] = sm.prow(3 + k)[lp];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) w[k] = sm.spt[(9 + k) * cnp + lp];
+    for (int k = 0; k < 3; ++k) w[k] = sm.prow(9 + k)[lp];
     double jp[2][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -738,8 +750,8 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? PSFM_SP_MINB : 1)) k_schu
   __syncthreads();
   if (tid < ti.np) {
     const double t0 = sm.sw[tid], t1 = sm.sw[cnp + tid], t2 = sm.sw[2 * cnp + tid];
-    const double h0 = sm.spt[3 * cnp + tid], h1 = sm.spt[4 * cnp + tid], h2 = sm.spt[5 * cnp + tid],
-                 h3 = sm.spt[6 * cnp + tid], h4 = sm.spt[7 * cnp + tid], h5 = sm.spt[8 * cnp + tid];
+    const double h0 = sm.prow(3)[tid], h1 = sm.prow(4)[tid], h2 = sm.prow(5)[tid],
+                 h3 = sm.prow(6)[tid], h4 = sm.prow(7)[tid], h5 = sm.prow(8)[tid];
     sm.sw[tid] = h0 * t0 + h1 * t1 + h2 * t2;
     sm.sw[cnp + tid] = h1 * t0 + h3 * t1 + h4 * t2;
     sm.sw[2 * cnp + tid] = h2 * t0 + h4 * t1 + h5 * t2;
@@ -799,31 +811,14 @@ struct BackArgs {
   int intr;
 };
 
+// One tile of the back-substitution.  Shared memory (sm.simg, sm.sx, sm.spt rows 0..11, sm.pstart) holds the tile's
+// staged inputs and is synchronised; the arguments are this thread's observation.  Ends with the tile's REDs.
 template <int TILE, bool ROT>
-__global__ void __launch_bounds__(TILE, (TILE == 256 ? 4 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<TILE> sm;
-  sm.carve(smem_raw, 3, 12, tc.cap_ns, tc.cap_np);
-  const TileInfo ti = tile_header(tc);
+__device__ __forceinline__ void back_substitute_tile(const TileCtx& tc, const BackArgs& a, TileSmem<TILE>& sm, const TileInfo& ti,
+                                                     const bool act, const int ls, const int lp, const double a00, const double a02,
+                                                     const double a12, const double r0, const double r1, const double* xk,
+                                                     const double inv_f) {
   const int tid = threadIdx.x;
-  const bool act = tid < ti.n;
-  const size_t M = tc.M;
-  const size_t i = (size_t)ti.base + tid;
-  int ls = 0, lp = 0;
-  double a00 = 0, a02 = 0, a12 = 0, r0 = 0, r1 = 0;
-  if (act) {
-    ls = __ldg(tc.obs_lseg + i);
-    lp = __ldg(tc.obs_lpt + i);
-    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
-    r0 = a.L.r[i]; r1 = a.L.r[M + i];
-  }
-  double xk[3] = {0, 0, 0};
-  double inv_f = 0.0;
-  if (a.intr >= 1) {
-    xk[0] = __ldg(a.xs + 6 * (size_t)tc.F); xk[1] = __ldg(a.xs + 6 * (size_t)tc.F + 1); xk[2] = __ldg(a.xs + 6 * (size_t)tc.F + 2);
-    inv_f = 1.0 / __ldg(a.K);
-  }
-  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, a.xs, a.X, a.ht, a.wt, false);
   ObsGeom g;
   double u0 = 0, u1 = 0, jf0 = 0, jf1 = 0, sq = 0;
 #pragma unroll
@@ -848,14 +843,14 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 4 : 1)) k_back_substitute
   if (tid < ti.np) {
     const size_t gp_ = (size_t)ti.pt0 + tid;
     const double t0 = sm.sw[tid], t1 = sm.sw[cnp + tid], t2 = sm.sw[2 * cnp + tid];
-    const double h0 = sm.spt[3 * cnp + tid], h1 = sm.spt[4 * cnp + tid], h2 = sm.spt[5 * cnp + tid],
-                 h3 = sm.spt[6 * cnp + tid], h4 = sm.spt[7 * cnp + tid], h5 = sm.spt[8 * cnp + tid];
+    const double h0 = sm.prow(3)[tid], h1 = sm.prow(4)[tid], h2 = sm.prow(5)[tid],
+                 h3 = sm.prow(6)[tid], h4 = sm.prow(7)[tid], h5 = sm.prow(8)[tid];
     // unscaled point update: dX = -(w^ - H~ t)
-    const double y0 = sm.spt[9 * cnp + tid] - (h0 * t0 + h1 * t1 + h2 * t2);
-    const double y1 = sm.spt[10 * cnp + tid] - (h1 * t0 + h3 * t1 + h4 * t2);
-    const double y2 = sm.spt[11 * cnp + tid] - (h2 * t0 + h4 * t1 + h5 * t2);
+    const double y0 = sm.prow(9)[tid] - (h0 * t0 + h1 * t1 + h2 * t2);
+    const double y1 = sm.prow(10)[tid] - (h1 * t0 + h3 * t1 + h4 * t2);
+    const double y2 = sm.prow(11)[tid] - (h2 * t0 + h4 * t1 + h5 * t2);
     sm.sw[tid] = y0; sm.sw[cnp + tid] = y1; sm.sw[2 * cnp + tid] = y2;
-    const double X0 = sm.spt[tid], X1 = sm.spt[cnp + tid], X2 = sm.spt[2 * cnp + tid];
+    const double X0 = sm.sxyz[3 * tid], X1 = sm.sxyz[3 * tid + 1], X2 = sm.sxyz[3 * tid + 2];
     const double c0 = X0 + (-y0), c1 = X1 + (-y1), c2 = X2 + (-y2);
     a.Xc[3 * gp_] = c0; a.Xc[3 * gp_ + 1] = c1; a.Xc[3 * gp_ + 2] = c2;
     const double e0 = X0 - c0, e1 = X1 - c1, e2 = X2 - c2;
@@ -877,6 +872,35 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 4 : 1)) k_back_substitute
   double v[3] = {mm, dx2, xc2};
   const double s = block_sum_multi<3>(v, sm.sred);
   if (tid < 3) atomicAdd(a.acc + tid, s);
+}
+
+template <int TILE, bool ROT>
+__global__ void __launch_bounds__(TILE, (TILE == 256 ? 4 : 1)) k_back_substitute(const TileCtx tc, const BackArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<TILE> sm;
+  sm.carve(smem_raw, 3, 12, tc.cap_ns, tc.cap_np);
+  const TileInfo ti = tile_header(tc);
+  const int tid = threadIdx.x;
+  const bool act = tid < ti.n;
+  const size_t M = tc.M;
+  const size_t i = (size_t)ti.base + tid;
+  int ls = 0, lp = 0;
+  double a00 = 0, a02 = 0, a12 = 0, r0 = 0, r1 = 0;
+  if (act) {
+    ls = __ldg(tc.obs_lseg + i);
+    lp = __ldg(tc.obs_lpt + i);
+    a00 = a.L.a[i]; a02 = a.L.a[M + i]; a12 = a.L.a[2 * M + i];
+    const double2 rr = reinterpret_cast<const double2*>(a.L.r)[i];
+    r0 = rr.x; r1 = rr.y;
+  }
+  double xk[3] = {0, 0, 0};
+  double inv_f = 0.0;
+  if (a.intr >= 1) {
+    xk[0] = __ldg(a.xs + 6 * (size_t)tc.F); xk[1] = __ldg(a.xs + 6 * (size_t)tc.F + 1); xk[2] = __ldg(a.xs + 6 * (size_t)tc.F + 2);
+    inv_f = 1.0 / __ldg(a.K);
+  }
+  tile_fill_smem<TILE>(tc, sm, ti, a.pose16, a.xs, a.X, a.ht, a.wt, false);
+  back_substitute_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, r0, r1, xk, inv_f);
 }
 
 // ------------------------------------------------------------------ K6: cost only

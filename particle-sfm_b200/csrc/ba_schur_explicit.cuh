@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_w(const T
     const int cnp = sm.cap_np;
     double hv[6], wkp[3];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+    for (int k = 0; k < 6; ++k) hv[k] = sm.prow(3 + k)[lp];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) wkp[k] = sm.spt[(9 + k) * cnp + lp];
+    for (int k = 0; k < 3; ++k) wkp[k] = sm.prow(9 + k)[lp];
     double jp[2][3], jc[2][6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -290,9 +290,9 @@ __device__ __forceinline__ void schur_tile_body(const TileCtx& tc, const StArgs&
     const int cnp = sm.cap_np;
     double hv[6], wkp[3], wh[3];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) hv[k] = sm.spt[(3 + k) * cnp + lp];
+    for (int k = 0; k < 6; ++k) hv[k] = sm.prow(3 + k)[lp];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { wkp[k] = sm.spt[(9 + k) * cnp + lp]; wh[k] = sm.spt[(12 + k) * cnp + lp]; }
+    for (int k = 0; k < 3; ++k) { wkp[k] = sm.prow(9 + k)[lp]; wh[k] = sm.prow(12 + k)[lp]; }
     double jp[2][3], jc[2][6], Q[2][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -503,21 +503,21 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile(cons
 template <int TILE, bool ROT>
 __global__ void __launch_bounds__(TILE, (TILE == 256 ? 2 : 1)) k_schur_tile_p(const TileCtx tc, const PipeSrc ps, const StArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int4 hdr_ring[4][2];
+  __shared__ __align__(16) int4 hdr_ring[4][2];
+  __shared__ __align__(8) unsigned long long bars[2];
   const int cns = tc.cap_ns, cnp = tc.cap_np;
   const size_t sb = PipeStage<TILE>::bytes(false, true, 15, cns, cnp);
   TileSmem<TILE> sm;
   sm.cap_ns = cns; sm.cap_np = cnp;
   sm.sv = reinterpret_cast<double*>(smem_raw + 2 * sb);
   sm.sw = nullptr; sm.sred = nullptr; sm.sx = nullptr;
-  pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, 15, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
-    view_stage<TILE>(sm, s, ti.base);
+  pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, bars, 15, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
+    view_stage<TILE>(sm, s);
     const int tid = threadIdx.x;
     const bool act = tid < ti.n;
-    const int off = ti.base & 1;
     int ls = 0, lp = 0;
     double a00 = 0, a02 = 0, a12 = 0;
-    if (act) { ls = s.lseg[off + tid]; lp = s.lpt[off + tid]; a00 = s.a[tid]; a02 = s.a[TILE + tid]; a12 = s.a[2 * TILE + tid]; }
+    if (act) { ls = s.lseg[tid]; lp = s.lpt[tid]; a00 = s.a0[tid]; a02 = s.a1[tid]; a12 = s.a2[tid]; }
     const int t0 = __ldg(a.tile_task + tile), nt = __ldg(a.tile_task + tile + 1) - t0;
     schur_tile_body<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, tile, t0, nt);
   });

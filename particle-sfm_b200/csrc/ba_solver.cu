@@ -150,6 +150,10 @@ struct psfm_ba_solver {
   DBuf<double> d_camrep, d_yrep;   // [NREP] replicas of the per-image accumulators (see ba_kernels.cuh)
   // explicit Schur complement (exact mode, ba_schur_explicit.cuh)
   bool pairs_ready = false;
+  // k_point_blocks of the current linearisation at this radius is already in d_hinv / d_w / d_prep (rank-local,
+  // not yet all-reduced): linearize_and_measure computes it for gradient_max_norm, compute_step reuses it
+  bool pb_fresh = false;
+  double pb_radius = 0.0;
   int nblocks = 0, nchunks = 0, bw = 0;
   long long npairs = 0;
   DBuf<unsigned long long> d_entries;
@@ -422,7 +426,7 @@ int build_structure(psfm_ba_solver* S) {
     PSFM_CUDA(cudaGetDevice(&dev));
     PSFM_CUDA(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, dev));
     S->d_tile_hdr.alloc(2 * (size_t)T, st); S->d_pstart_rel.alloc((size_t)P + 1, st);
-    S->d_cseg_off32.alloc((size_t)S->nseg + 1, st); S->d_seg_pose.alloc(12 * (size_t)S->nseg + 2, st);
+    S->d_cseg_off32.alloc((size_t)S->nseg + 1, st); S->d_seg_pose.alloc(PSFM_SPS * (size_t)S->nseg + 2, st); S->d_seg_pose.zero(st);
     k_pipe_headers<<<grid_for(T), 256, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_cseg_ptr.p, T, S->d_tile_hdr.p);
     PSFM_LAUNCH_CHECK();
     k_pipe_pstart<<<T, 128, 0, st>>>(S->d_tile_start.p, S->d_tile_pt.p, S->d_pt_ptr.p, T, S->d_pstart_rel.p);
@@ -715,8 +719,11 @@ void cam_finalize(psfm_ba_solver* S, const RunCfg& c, double radius, bool fused)
 // fused_explicit: the rhs correction comes out of k_schur_tile (do_explicit_solve_fused), the
 // Schur-Jacobi blocks are not needed; only the point blocks and the intrinsics sums are made here
 void do_reduced_setup(psfm_ba_solver* S, const RunCfg& c, double radius, bool fused_explicit = false) {
-  S->d_prep.zero(S->stream);
-  do_point_blocks(S, c, radius);
+  if (!(S->pb_fresh && S->pb_radius == radius)) {
+    S->d_prep.zero(S->stream);
+    do_point_blocks(S, c, radius);
+  }
+  S->pb_fresh = false;           // d_prep is all-reduced in place below
   if (fused_explicit) {
     dist::allreduce_sum(S->d_prep.p, S->d_prep.n, S->stream);
     return;
@@ -850,6 +857,7 @@ LinOut linearize_and_measure(psfm_ba_solver* S, const RunCfg& c, double radius, 
   S->d_gmax.zero(S->stream);
   S->d_prep.zero(S->stream);
   do_point_blocks(S, c, radius);
+  S->pb_fresh = true; S->pb_radius = radius;
   dist::allreduce_max(S->d_gmax.p, 1, S->stream);
   do_cam_gmax(S);
   d2h(S, &S->hs->lin_cost, S->d_lin.p + (size_t)S->F * NVL + (size_t)S->C * NVI, 1);
@@ -877,7 +885,7 @@ __global__ void k_point_span(const int* pt_ptr, const int* obs_img, int P, int* 
 // The fused path ends in Sband: when the band is narrow enough for the register window of
 // k_band_chol, the reduced system never exists as a dense matrix.
 void setup_band_chol(psfm_ba_solver* S) {
-  const BandPlan pl = band_chol_plan(6 * S->F, S->bw);
+  const BandPlan pl = band_chol_plan(6 * S->F, S->bw, S->span);
   S->band_chol = S->fused && pl.W > 0 && !getenv("PSFM_OLD_CHOL");
   if (!S->band_chol) {
     S->d_S.alloc((size_t)(S->NS + 1) * (S->NS + 1), S->stream);
@@ -1187,9 +1195,11 @@ void launch_band_cholesky(psfm_ba_solver* S) {
   c.prof = want_prof ? reinterpret_cast<long long*>(S->d_cholprof.p) : nullptr;
   band_chol_launch(c, st);
   if (want_prof) {
-    long long h[8];
+    long long h[16];
     PSFM_CUDA(cudaStreamSynchronize(st));
     PSFM_CUDA(cudaMemcpy(h, S->d_cholprof.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (c.blk6) fprintf(stderr, "[psfm chol6 cycles/step] worker0 update %.0f recycle %.0f publish %.0f | panel pbar %.0f chol+solve %.0f out %.0f (steps %lld)\n",
+                        h[8] / (h[3] / 6.0), h[9] / (h[3] / 6.0), h[10] / (h[3] / 6.0), h[11] / (h[3] / 6.0), h[12] / (h[3] / 6.0), h[13] / (h[3] / 6.0), h[3] / 6);
     const double np_ = (double)std::max(1ll, h[3]);
     fprintf(stderr, "[psfm band chol cycles] factor %lld (%lld pivots, %.0f / pivot) corner+stage %lld backsub %lld | per pivot own/wait: helper %.0f/%.0f worker0 %.0f/%.0f\n",
             h[0], h[3], (double)h[0] / np_, h[1], h[2], h[4] / np_, h[5] / np_, h[6] / np_, h[7] / np_);
@@ -1321,7 +1331,19 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   BackArgs b;
   b.L = lin_of(S); b.pose16 = S->d_pose16.p; b.X = S->d_X[S->cur].p; b.ht = S->d_hinv.p; b.wt = S->d_w.p;
   b.xs = S->d_xs.p; b.K = S->d_K[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
-  PSFM_TILE_LAUNCH(k_back_substitute, 3, 12, S, c.rot, b);
+  {
+    g_bs_nxs = S->NS;
+    const size_t lin_smem = S->tile == 256 ? pipe_smem_linearize<256>(S->cap_ns, S->cap_np) : pipe_smem_linearize<512>(S->cap_ns, S->cap_np);
+    const size_t bs_smem = S->tile == 256 ? pipe_smem_back_substitute<256>(S->cap_ns, S->cap_np) : pipe_smem_back_substitute<512>(S->cap_ns, S->cap_np);
+    static const bool no_pipe = getenv("PSFM_NO_PIPE_BACK") != nullptr;
+    if (!no_pipe && pipe_ok(S, lin_smem) && pipe_ok(S, bs_smem)) {     // seg_pose exists iff the sweep was pipelined
+      PipeSrc ps = pipe_src(S);
+      ps.obs_xy = reinterpret_cast<const double2*>(S->d_r.p); ps.obs_a = S->d_a.p; ps.p6 = S->d_hinv.p; ps.p3a = S->d_w.p;
+      PSFM_PIPE_LAUNCH(k_back_substitute_p, pipe_smem_back_substitute, S, c.rot, ps, b);
+    } else {
+      PSFM_TILE_LAUNCH(k_back_substitute, 3, 12, S, c.rot, b);
+    }
+  }
   ApplyArgs a;
   a.yc = S->d_x.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
   a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
@@ -1452,6 +1474,7 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
   const double t0 = now_s();
   S->events.reset(); S->ev_lin.clear(); S->ev_sp.clear(); S->ev_sw.clear(); S->ev_pairs.clear(); S->ev_chol.clear();
   upload_state(S);
+  S->pb_fresh = false;
   set_masks_and_unit_scale(S, c);
   s.num_residuals_reduced = 2 * M_all;
   s.num_effective_parameters_reduced = c.num_effective_parameters + 3 * count_observed_points_all_ranks(S);
@@ -1710,8 +1733,8 @@ extern "C" int psfm_ba_evaluate(psfm_ba_solver* S, const psfm_ba_options* opts, 
     if (residuals) memset(residuals, 0, sizeof(double) * 2 * (size_t)S->M0);      // filtered observations: 0
     if (residuals)
       for (size_t j = 0; j < M; ++j) {
-        residuals[2 * (size_t)obs_orig[j]] = r[j];
-        residuals[2 * (size_t)obs_orig[j] + 1] = r[M + j];
+        residuals[2 * (size_t)obs_orig[j]] = r[2 * j];
+        residuals[2 * (size_t)obs_orig[j] + 1] = r[2 * j + 1];
       }
     if (gradient_cam) {
       for (size_t i = 0; i < F; ++i)

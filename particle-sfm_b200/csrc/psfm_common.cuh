@@ -65,11 +65,11 @@ struct DBuf {
     if (count == 0) count = 1;
     if (stream) {
       keep_pool_memory();
-      PSFM_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+      PSFM_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T) + 64, stream));   // slack: bulk copies read whole 16-byte windows
       st = stream;
       async = true;
     } else {
-      PSFM_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+      PSFM_CUDA(cudaMalloc((void**)&p, count * sizeof(T) + 64));
       async = false;
     }
   }

@@ -37,7 +37,10 @@ def _solve(A, b, nb, bw):
 # (nb, bw): tiny window, window wider than the matrix, nb not a multiple of 4, the bench shape
 # (6 * 200 images, span 11/12), the 1024-thread instantiation, the widest supported window
 CASES = [(30, 9), (18, 17), (18, 40), (90, 59), (1200, 71), (1200, 77), (600, 127), (3000, 71), (700, 150), (100, 31), (1203, 95),
-         (64, 6), (41, 14), (500, 38)]
+         (64, 6), (41, 14), (500, 38),
+         # block-6 kernel (nb and bw + 1 multiples of 6): window = matrix, one-sided, two-sided, the 512-thread
+         # instantiation, the widest window (25 blocks), a window of 3 blocks, identity padding past the matrix
+         (36, 17), (36, 35), (900, 35), (1200, 95), (1200, 149), (150, 149), (2400, 23), (78, 17), (1200, 83)]
 
 
 @pytest.mark.parametrize("nb,bw", CASES)
@@ -96,3 +99,37 @@ def test_two_sided_and_one_sided_forms_agree(gpu):
         out[name] = np.load(path)
     assert np.abs(out["two"] - out["one"]).max() <= 1e-12 * np.abs(out["one"]).max()
     assert not np.array_equal(out["two"], out["one"])      # a different elimination order: not the same bits
+
+
+@pytest.mark.parametrize("bad", [0, 57, 281, 282, 299, 317, 318, 450, 599])
+def test_block6_two_sided_form_reports_a_bad_pivot_wherever_it_is(gpu, bad):
+    """nb = 600, bw = 35: block-6 kernel, window of 6 image blocks, two CTAs (top-down 47 blocks, bottom-up 47, 6 in
+    the middle)."""
+    A, b = _system(600, 35, seed=5)
+    rc, x = _solve(A, b, 600, 35)
+    assert rc == 0
+    ref = np.linalg.solve(A, b)
+    assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
+    A[bad, bad] = -1.0
+    rc, _ = _solve(A, b, 600, 35)
+    assert rc == -1
+
+
+def test_block6_forms_agree(gpu):
+    """Block-6 two-sided (default) vs block-6 one-sided vs the rank-1 kernel on the bench shape (child processes:
+    the switches are read once per process)."""
+    import os
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path[:0] = [%r, %r]; from test_gpu_band_chol import _system, _solve;"
+            "A, b = _system(1200, 71, seed=11); rc, x = _solve(A, b, 1200, 71); assert rc == 0; np.save(sys.argv[1], x)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for name, env in (("b6two", {}), ("b6one", {"PSFM_CHOL_ONE_SIDED": "1"}), ("rank1", {"PSFM_CHOL_RANK1": "1"})):
+        path = os.path.join(root, "gpurun_out", f"_band_{name}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests")), path], check=True, env={**os.environ, **env}, cwd=root)
+        out[name] = np.load(path)
+    scale = np.abs(out["rank1"]).max()
+    assert np.abs(out["b6two"] - out["rank1"]).max() <= 1e-12 * scale
+    assert np.abs(out["b6one"] - out["rank1"]).max() <= 1e-12 * scale
