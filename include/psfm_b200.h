@@ -146,6 +146,26 @@ int psfm_tracker_buffer_inputs(const float* flow01, const float* flow02, const u
                                const double* x0, int32_t n, double upper_flow, double* ref1, double* ref2, double* scale);
 
 /* ------------------------------------------------------------------------- */
+/* the RANSAC-free steps that initialise HP2, batched (csrc/init_geometry.cu). */
+/* Host buffers in, host buffers out.                                          */
+/* ------------------------------------------------------------------------- */
+/* BatchOptimizeRelativePositionWithKnownRotation (sfm/gmapper/src/global/known_rotation_util.cc:198-229) for
+   num_pairs image pairs at once; per pair OptimizeRelativePositionWithKnownRotation (:107-196): IRLS on the
+   epipolar constraints with the two known rotations, sign by the cheirality majority.
+   points1 / points2: [pair_ptr[num_pairs]][2] NORMALISED image points (camera.ImageToWorld, :215-221) of the
+   correspondences, pair p owns the range pair_ptr[p] .. pair_ptr[p + 1]; qvec1 / qvec2: [num_pairs][4] (w, x, y, z);
+   tvec: [num_pairs][3] unit relative positions (pair.tvec); iterations (may be NULL): IRLS iterations run */
+int psfm_known_rotation_translations(const double* points1, const double* points2, const int32_t* pair_ptr,
+                                     const double* qvec1, const double* qvec2, int32_t num_pairs, double* tvec,
+                                     int32_t* iterations);
+/* Multi-view DLT of num_tracks tracks at once: COLMAP TriangulateMultiViewPoint, the estimator behind
+   IncrementalTriangulator::Create (sfm/incremental_triangulator.cc:463-548) without its RANSAC loop.
+   proj_matrices: [track_ptr[num_tracks]][12] row-major 3 x 4 (image.ProjectionMatrix(), :494), points: [..][2]
+   normalised image points (:492-493), track t owns the range track_ptr[t] .. track_ptr[t + 1]; xyz: [num_tracks][3] */
+int psfm_triangulate_tracks(const double* proj_matrices, const double* points, const int32_t* track_ptr,
+                            int32_t num_tracks, double* xyz);
+
+/* ------------------------------------------------------------------------- */
 /* HP2 — global bundle adjustment                                             */
 /* ------------------------------------------------------------------------- */
 

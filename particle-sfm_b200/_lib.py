@@ -20,7 +20,7 @@ EXPORTS = [
     "psfm_ba_linear_step", "psfm_ba_band_solve", "psfm_measure_dfma", "psfm_ba_default_refine_options",
     "psfm_ba_filter_negative_depth", "psfm_ba_filter_points", "psfm_ba_normalize", "psfm_ba_num_observations",
     "psfm_ba_get_observation_mask", "psfm_ba_get_point_errors", "psfm_ba_iterative_refinement",
-    "psfm_grid_sample", "psfm_flow_check", "psfm_tracker_step", "psfm_tracker_buffer_inputs", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
+    "psfm_grid_sample", "psfm_flow_check", "psfm_tracker_step", "psfm_tracker_buffer_inputs", "psfm_known_rotation_translations", "psfm_triangulate_tracks", "psfm_dist_get_unique_id", "psfm_dist_init", "psfm_dist_world_size",
     "psfm_dist_rank", "psfm_dist_finalize",
 ]
 
@@ -67,6 +67,8 @@ def lib():
     L.psfm_flow_check.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_float, fp, u8p]
     L.psfm_tracker_step.argtypes = [fp, u8p, C.c_int32, C.c_int32, dp, C.c_int32, C.c_int32, dp, u8p, u8p]
     L.psfm_tracker_buffer_inputs.argtypes = [fp, fp, u8p, C.c_int32, C.c_int32, dp, C.c_int32, C.c_double, dp, dp, dp]
+    L.psfm_known_rotation_translations.argtypes = [dp, dp, ip, dp, dp, C.c_int32, dp, ip]
+    L.psfm_triangulate_tracks.argtypes = [dp, dp, ip, C.c_int32, dp]
     i64p = C.POINTER(C.c_int64)
     L.psfm_ba_default_refine_options.argtypes = [C.POINTER(_abi.BARefineOptions)]
     L.psfm_ba_default_refine_options.restype = None

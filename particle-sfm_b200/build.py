@@ -29,6 +29,7 @@ UNITS = [
     ("common.cu", []),
     ("microbench.cu", []),
     ("tracker.cu", []),
+    ("init_geometry.cu", []),
     ("dist.cu", []),
     ("ba_solver.cu", []),
     ("traj_solver.cu", ["-fmad=false"]),
