@@ -373,7 +373,7 @@ def main():
         "k_schur_product (implicit S*p, one per PCG iteration)": dict(bound="hbm", ms=sum(s.schur_product_ms for s in summaries),
                                                                       n=sum(s.num_schur_products for s in summaries),
                                                                       bytes=(28 + 72.0 / Lmean) * M_local),
-        "k_band_assemble + k_band_chol (reduced system: assemble, factor, solve; one CTA)": dict(
+        "k_band_assemble + k_band_chol6 (reduced system: fold, all-reduce, assemble, block-6 factor, solve; two CTAs)": dict(
             bound="latency", ms=sum(s.cholesky_ms for s in summaries), n=n_expl, bytes=None),
     }
     if fused:
@@ -392,7 +392,7 @@ def main():
     traffic = {}
     try:
         if world == 1 and args.config == "target" and not args.points:
-            with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "traffic_r02b.json")) as f:
                 traffic = json.load(f)
     except (OSError, ValueError):
         traffic = {}
@@ -416,7 +416,7 @@ def main():
             d["frac"] = d["achieved"] / peak
         else:
             d.update({"peak": None, "unit": None, "achieved": None, "frac": None,
-                      "note": "a chain of 6F dependent pivots in one CTA: bounded by the latency of one pivot step, not by bandwidth or flops"})
+                      "note": "a chain of F dependent 6 x 6 block pivots per side (two CTAs, top-down and bottom-up): bounded by the latency of one block step (shared-memory wavefronts of the rank-6 window update + the 6-pivot LDL' chain), not by bandwidth or flops"})
         return d
     ranked = sorted((n for n in kernels if kernels[n]["bound"] != "latency" and kernels[n]["n"]), key=lambda n: -kernels[n]["ms"])
     roofline = roof(ranked[0]) if ranked else None
