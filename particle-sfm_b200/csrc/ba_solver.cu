@@ -1346,22 +1346,8 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   S->d_step.zero(S->stream);
   S->d_rep.zero(S->stream);
   scale_vec(S, S->d_x.p, nullptr);
-  BackArgs b;
-  b.L = lin_of(S); b.pose16 = S->d_pose16.p; b.X = S->d_X[S->cur].p; b.ht = S->d_hinv.p; b.wt = S->d_w.p;
-  b.xs = S->d_xs.p; b.K = S->d_K[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
-  {
-    g_bs_nxs = S->NS;
-    const size_t lin_smem = S->tile == 256 ? pipe_smem_linearize<256>(S->cap_ns, S->cap_np) : pipe_smem_linearize<512>(S->cap_ns, S->cap_np);
-    const size_t bs_smem = S->tile == 256 ? pipe_smem_back_substitute<256>(S->cap_ns, S->cap_np) : pipe_smem_back_substitute<512>(S->cap_ns, S->cap_np);
-    static const bool no_pipe = getenv("PSFM_NO_PIPE_BACK") != nullptr;
-    if (!no_pipe && pipe_ok(S, lin_smem) && pipe_ok(S, bs_smem)) {     // seg_pose exists iff the sweep was pipelined
-      PipeSrc ps = pipe_src(S);
-      ps.obs_xy = reinterpret_cast<const double2*>(S->d_r.p); ps.obs_a = S->d_a.p; ps.p6 = S->d_hinv.p; ps.p3a = S->d_w.p;
-      PSFM_PIPE_LAUNCH(k_back_substitute_p, pipe_smem_back_substitute, S, c.rot, ps, b);
-    } else {
-      PSFM_TILE_LAUNCH(k_back_substitute, 3, 12, S, c.rot, b);
-    }
-  }
+  // candidate poses / intrinsics first: they only need the reduced-system solution, and the pipelined
+  // back-substitution can then evaluate the candidate cost in the same sweep (no k_cost pass over the observations)
   ApplyArgs a;
   a.yc = S->d_x.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
   a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
@@ -1370,7 +1356,35 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   const int n = S->F + S->C;
   k_apply_cams<<<(n + 255) / 256, 256, 0, S->stream>>>(a);
   PSFM_LAUNCH_CHECK();
-  if (S->M) {
+  BackArgs b;
+  b.L = lin_of(S); b.pose16 = S->d_pose16.p; b.X = S->d_X[S->cur].p; b.ht = S->d_hinv.p; b.wt = S->d_w.p;
+  b.xs = S->d_xs.p; b.K = S->d_K[S->cur].p; b.Xc = S->d_X[1 - S->cur].p; b.acc = S->d_step.p; b.intr = c.intr;
+  b.pose_c = nullptr; b.K_c = S->d_K[1 - S->cur].p;
+  b.loss.type = c.o.loss_function_type; b.loss.a = c.o.loss_function_scale;
+  bool cost_fused = false;
+  {
+    g_bs_nxs = S->NS;
+    static const bool no_pipe = getenv("PSFM_NO_PIPE_BACK") != nullptr, no_fuse = getenv("PSFM_FUSED_COST") == nullptr;
+    const size_t lin_smem = S->tile == 256 ? pipe_smem_linearize<256>(S->cap_ns, S->cap_np) : pipe_smem_linearize<512>(S->cap_ns, S->cap_np);
+    auto bs_bytes = [&]() { return S->tile == 256 ? pipe_smem_back_substitute<256>(S->cap_ns, S->cap_np) : pipe_smem_back_substitute<512>(S->cap_ns, S->cap_np); };
+    // fused cost (opt-in, PSFM_FUSED_COST=1): the candidate pose table (8 F doubles) lives in shared memory; at least
+    // two CTAs per SM must fit.  Measured on the bench workload: 16.61 ms per solve fused against 16.57 ms with the
+    // separate k_cost pass — the table and the second 16-byte stage cost the third resident CTA, which cancels the
+    // 0.085 ms of k_cost.  Kept for problems with few images; off by default.
+    g_bs_fuse_F = no_fuse ? 0 : S->F;
+    if (g_bs_fuse_F && !(pipe_ok(S, bs_bytes()) && (S->tile != 256 || 2 * (bs_bytes() + 1024) <= (size_t)227 * 1024))) g_bs_fuse_F = 0;
+    const size_t bs_smem = bs_bytes();
+    if (!no_pipe && pipe_ok(S, lin_smem) && pipe_ok(S, bs_smem)) {     // seg_pose exists iff the sweep was pipelined
+      PipeSrc ps = pipe_src(S);
+      ps.obs_xy = reinterpret_cast<const double2*>(S->d_r.p); ps.obs_a = S->d_a.p; ps.p6 = S->d_hinv.p; ps.p3a = S->d_w.p;
+      if (g_bs_fuse_F) { ps.obs_xy2 = S->d_obs_xy.p; b.pose_c = S->d_pose[1 - S->cur].p; cost_fused = true; }
+      PSFM_PIPE_LAUNCH(k_back_substitute_p, pipe_smem_back_substitute, S, c.rot, ps, b);
+    } else {
+      g_bs_fuse_F = 0;
+      PSFM_TILE_LAUNCH(k_back_substitute, 3, 12, S, c.rot, b);
+    }
+  }
+  if (S->M && !cost_fused) {
     CostArgs ca;
     ca.pose = S->d_pose[1 - S->cur].p; ca.X = S->d_X[1 - S->cur].p; ca.K = S->d_K[1 - S->cur].p;
     ca.loss.type = c.o.loss_function_type; ca.loss.a = c.o.loss_function_scale;
