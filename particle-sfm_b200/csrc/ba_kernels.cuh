@@ -342,9 +342,13 @@ struct LinArgs {
 // One tile of the Jacobian sweep.  Shared memory (sm.simg, sm.spt, sm.pstart, sm.coff, sm.cimg,
 // sm.perm) holds the tile's staged inputs and is synchronised; ls / lp / xy are this thread's
 // observation.  Ends without a barrier.
+// racc (optional, shared memory [3][TILE]): the persistent kernel accumulates the block-wide sums (cost, focal terms)
+// per THREAD across its tiles and reduces them once at the end (linearize_flush) instead of a barrier pair per tile;
+// the principal-point sums (intr == 3: not what the pipeline runs) keep their per-tile block sum.
 template <int TILE, bool ROT>
 __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs& a, TileSmem<TILE>& sm, const TileInfo& ti,
-                                               const bool act, const int ls, const int lp, const double2 xy, const int rep) {
+                                               const bool act, const int ls, const int lp, const double2 xy, const int rep,
+                                               double* racc = nullptr) {
   const int tid = threadIdx.x;
   const size_t M = tc.M;
   const size_t i = (size_t)ti.base + tid;
@@ -465,25 +469,44 @@ __device__ __forceinline__ void linearize_tile(const TileCtx& tc, const LinArgs&
     v[0] = cost;
     v[1] = jf0 * jf0 + jf1 * jf1;
     v[2] = jf0 * r0 + jf1 * r1;
-    const double s = block_sum_multi<3>(v, sm.sred);
-    if (tid == 0) atomicAdd(a.acc_cost, s);
-    if (a.intr >= 1) {
-      if (tid == 1) atomicAdd(a.acc_intr + 0, s);
-      if (tid == 2) atomicAdd(a.acc_intr + 6, s);
+    double u[7];
+    u[0] = jf0 * sq;                 // f-cx
+    u[1] = jf1 * sq;                 // f-cy
+    u[2] = act ? sq * sq : 0.0;      // cx-cx
+    u[3] = 0.0;                      // cx-cy
+    u[4] = act ? sq * sq : 0.0;      // cy-cy
+    u[5] = sq * r0;                  // g cx
+    u[6] = sq * r1;                  // g cy
+    if (racc != nullptr) {
+      // per-thread running sums in shared memory (stride TILE; registers are what this kernel has least of)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) racc[k * TILE + tid] += v[k];
+    } else {
+      const double s = block_sum_multi<3>(v, sm.sred);
+      if (tid == 0) atomicAdd(a.acc_cost, s);
+      if (a.intr >= 1) {
+        if (tid == 1) atomicAdd(a.acc_intr + 0, s);
+        if (tid == 2) atomicAdd(a.acc_intr + 6, s);
+      }
     }
     if (a.intr == 3) {
-      double u[7];
-      u[0] = jf0 * sq;                 // f-cx
-      u[1] = jf1 * sq;                 // f-cy
-      u[2] = act ? sq * sq : 0.0;      // cx-cx
-      u[3] = 0.0;                      // cx-cy
-      u[4] = act ? sq * sq : 0.0;      // cy-cy
-      u[5] = sq * r0;                  // g cx
-      u[6] = sq * r1;                  // g cy
       const double s2 = block_sum_multi<7>(u, sm.sred);
       if (tid < 5) atomicAdd(a.acc_intr + 1 + tid, s2);
       else if (tid < 7) atomicAdd(a.acc_intr + 7 + (tid - 5), s2);
     }
+  }
+}
+
+// the deferred sums of a persistent CTA (racc of linearize_tile) -> global accumulators
+template <int TILE>
+__device__ __forceinline__ void linearize_flush(const LinArgs& a, const double* racc, double* sred) {
+  const int tid = threadIdx.x;
+  double v[3] = {racc[tid], racc[TILE + tid], racc[2 * TILE + tid]};
+  const double s = block_sum_multi<3>(v, sred);
+  if (tid == 0) atomicAdd(a.acc_cost, s);
+  if (a.intr >= 1) {
+    if (tid == 1) atomicAdd(a.acc_intr + 0, s);
+    if (tid == 2) atomicAdd(a.acc_intr + 6, s);
   }
 }
 
@@ -822,7 +845,7 @@ __device__ __forceinline__ void back_substitute_tile(const TileCtx& tc, const Ba
                                                      const bool act, const int ls, const int lp, const double a00, const double a02,
                                                      const double a12, const double r0, const double r1, const double* xk,
                                                      const double inv_f, const double* pose_sm = nullptr,
-                                                     const double2 xy = double2{0.0, 0.0}) {
+                                                     const double2 xy = double2{0.0, 0.0}, double* racc = nullptr) {
   const int tid = threadIdx.x;
   ObsGeom g;
   double u0 = 0, u1 = 0, jf0 = 0, jf1 = 0, sq = 0;
@@ -894,6 +917,11 @@ __device__ __forceinline__ void back_substitute_tile(const TileCtx& tc, const Ba
     cc = 0.5 * rho0;
   }
   double v[4] = {mm, dx2, xc2, cc};
+  if (racc != nullptr) {       // persistent kernel: per-thread sums (shared memory, stride TILE) across its tiles, one reduction at the end
+#pragma unroll
+    for (int k = 0; k < 4; ++k) racc[k * TILE + tid] += v[k];
+    return;
+  }
   const double s = block_sum_multi<4>(v, sm.sred);
   if (tid < (pose_sm != nullptr ? 4 : 3)) atomicAdd(a.acc + tid, s);
 }

@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize_p(con
   sm.sw = nullptr;
   sm.sred = sm.sv + 18 * PSFM_SVS;
   sm.sx = nullptr;
+  double* racc = sm.sred + 9 * 32;          // [3][TILE] running sums of this CTA's threads
+  for (int k = 0; k < 3; ++k) racc[k * TILE + threadIdx.x] = 0.0;
   pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, bars, 3, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
     view_stage<TILE>(sm, s);
     const int tid = threadIdx.x;
@@ -286,13 +288,14 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_linearize_p(con
     int ls = 0, lp = 0;
     double2 xy = make_double2(0.0, 0.0);
     if (act) { ls = s.lseg[tid]; lp = s.lpt[tid]; xy = s.xy[tid]; }
-    linearize_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, xy, tile);
+    linearize_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, xy, tile, racc);
   });
+  if ((int)blockIdx.x < tc.T) linearize_flush<TILE>(a, racc, sm.sred);
 }
 
 template <int TILE>
 inline size_t pipe_smem_linearize(int cns, int cnp) {
-  return 2 * PipeStage<TILE>::bytes(true, false, 3, cns, cnp) + sizeof(double) * (18 * (TILE + 1) + 9 * 32);
+  return 2 * PipeStage<TILE>::bytes(true, false, 3, cns, cnp) + sizeof(double) * (18 * (TILE + 1) + 9 * 32 + 3 * TILE);
 }
 
 
@@ -328,6 +331,8 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute
     xk[0] = __ldg(a.xs + 6 * (size_t)tc.F); xk[1] = __ldg(a.xs + 6 * (size_t)tc.F + 1); xk[2] = __ldg(a.xs + 6 * (size_t)tc.F + 2);
     inv_f = 1.0 / __ldg(a.K);
   }
+  double* racc = pose_all + (fuse ? 8 * (size_t)tc.F : 0);       // [4][TILE] running sums of this CTA's threads
+  for (int k = 0; k < 4; ++k) racc[k * TILE + threadIdx.x] = 0.0;
   __syncthreads();
   pipe_run<TILE>(tc, ps, smem_raw, hdr_ring, bars, 12, cns, cnp, [&](const TileInfo& ti, const PipeStage<TILE>& s, int tile) {
     view_stage<TILE>(sm, s);
@@ -348,8 +353,13 @@ __global__ void __launch_bounds__(TILE, (TILE == 256 ? 3 : 1)) k_back_substitute
       sm.sx[k * cns + sg] = xs_all[6 * s.cimg[sg] + k];
     }
     __syncthreads();
-    back_substitute_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, r0, r1, xk, inv_f, fuse ? pose_all : nullptr, xy);
+    back_substitute_tile<TILE, ROT>(tc, a, sm, ti, act, ls, lp, a00, a02, a12, r0, r1, xk, inv_f, fuse ? pose_all : nullptr, xy, racc);
   });
+  if ((int)blockIdx.x < tc.T) {
+    double v[4] = {racc[threadIdx.x], racc[TILE + threadIdx.x], racc[2 * TILE + threadIdx.x], racc[3 * TILE + threadIdx.x]};
+    const double s = block_sum_multi<4>(v, sm.sred);
+    if (threadIdx.x < (fuse ? 4 : 3)) atomicAdd(a.acc + threadIdx.x, s);
+  }
 }
 
 inline int g_bs_nxs = 0;      // 6 F + 3 C of the solver being launched (set by the caller: the launch macro passes two sizes)
@@ -357,7 +367,7 @@ inline int g_bs_fuse_F = 0;   // > 0: the candidate cost is fused (pose table of
 template <int TILE>
 inline size_t pipe_smem_back_substitute(int cns, int cnp) {
   return 2 * PipeStage<TILE>::bytes(true, true, 12, cns, cnp, g_bs_fuse_F > 0) +
-         sizeof(double) * (3 * (TILE + 1) + 4 * (size_t)cnp + 9 * 32 + 6 * (size_t)cns + (size_t)g_bs_nxs + 2 + 8 * (size_t)g_bs_fuse_F);
+         sizeof(double) * (3 * (TILE + 1) + 4 * (size_t)cnp + 9 * 32 + 6 * (size_t)cns + (size_t)g_bs_nxs + 2 + 8 * (size_t)g_bs_fuse_F + 4 * TILE);
 }
 
 }  // namespace ba
