@@ -63,6 +63,30 @@ __global__ void k_fold_replicas(double* __restrict__ dst, double* __restrict__ r
   dst[i] = scale ? scale[i] * s : s;
 }
 
+// two folds in one launch (the camera-side sums and the band blocks of the fused Schur kernel)
+__global__ void k_fold_replicas2(double* __restrict__ dst, double* __restrict__ rep_a, size_t na, int nrep_a, double* __restrict__ rep_b,
+                                 size_t nb, int nrep_b) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na + nb) return;
+  double* rep = rep_a;
+  size_t stride = na;
+  int nrep = nrep_a;
+  double* out = dst + i;
+  if (i >= na) { i -= na; rep = rep_b; stride = nb; nrep = nrep_b; }
+  double s = 0.0;
+  for (int r0 = 0; r0 < nrep; r0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (r0 + u < nrep) ? rep[(size_t)(r0 + u) * stride + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < nrep) rep[(size_t)(r0 + u) * stride + i] = 0.0;
+  }
+  *out = s;
+}
+
 // xs = s o x  (the tile kernels work with the unscaled Jacobian: J_scaled x = J (s o x))
 __global__ void k_scale_vec(const double* x, const double* scale, size_t n, double* xs, const int* skip_flag) {
   if (skip_flag && *skip_flag != 0) return;

@@ -48,7 +48,7 @@ struct HostScalars {   // pinned
   double gmax;
   double prep_fail;
   double step[4];      // sum m(r+m/2), |dX|^2, |Xc|^2, candidate cost
-  double rep[2];       // |dcam|^2, |cam_c|^2
+  double rep[2];       // |dcam|^2, |cam_c|^2   (must follow step: one copy of six doubles, compute_step)
   double x2;
   PcgState pcg;
   int chol_fail;
@@ -452,7 +452,7 @@ void alloc_work(psfm_ba_solver* S) {
   S->d_scale_c.alloc(NS, S->stream); S->d_scale_p.alloc(3 * P, S->stream);
   S->d_lin.alloc(F * NVL + C * NVI + 1, S->stream);
   S->d_prep.alloc(F * NVL + C * NVI + 1, S->stream);
-  S->d_step.alloc(4, S->stream); S->d_rep.alloc(2, S->stream); S->d_gmax.alloc(1, S->stream); S->d_x2.alloc(1, S->stream);
+  S->d_step.alloc(8, S->stream); S->d_rep.alloc(2, S->stream); S->d_gmax.alloc(1, S->stream); S->d_x2.alloc(1, S->stream);
   S->d_Dc2.alloc(NS, S->stream); S->d_Minv.alloc(9 * (size_t)S->NB, S->stream); S->d_rhs.alloc(NS, S->stream);
   S->d_x.alloc(NS, S->stream); S->d_rv.alloc(NS, S->stream); S->d_p.alloc(NS, S->stream); S->d_z.alloc(NS, S->stream); S->d_y.alloc(NS, S->stream); S->d_zero.alloc(NS, S->stream);
   S->d_zero.zero(S->stream);
@@ -1252,8 +1252,7 @@ void do_explicit_solve_fused(psfm_ba_solver* S, const RunCfg& c, double radius) 
   }
   mark(S->ev_sw, false);
   mark(S->ev_chol, true);
-  fold_replicas(S, S->d_xband.p, S->d_xcamrep.p, nx, nullptr, nullptr);
-  k_fold_replicas<<<grid_for(S->band_n), 256, 0, st>>>(S->d_xband.p + nx, S->d_bandrep.p, S->band_n, S->band_n, S->band_nrep, nullptr, nullptr);
+  k_fold_replicas2<<<grid_for(nx + S->band_n), 256, 0, st>>>(S->d_xband.p, S->d_xcamrep.p, nx, NREP, S->d_bandrep.p, S->band_n, S->band_nrep);
   PSFM_LAUNCH_CHECK();
   dist::allreduce_sum(S->d_xband.p, S->d_xband.n, st);
   cam_finalize(S, c, radius, true);
@@ -1343,8 +1342,7 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   }
   so.pcg_iters = iters;
   // candidate: points (inside the back-substitution), poses/intrinsics, cost
-  S->d_step.zero(S->stream);
-  S->d_rep.zero(S->stream);
+  S->d_step.zero(S->stream);          // [0..3] step scalars, [4..5] the camera share (k_apply_cams): one memset
   scale_vec(S, S->d_x.p, nullptr);
   // candidate poses / intrinsics first: they only need the reduced-system solution, and the pipelined
   // back-substitution can then evaluate the candidate cost in the same sweep (no k_cost pass over the observations)
@@ -1352,7 +1350,7 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
   a.yc = S->d_x.p; a.scale_c = S->d_scale_c.p; a.active = S->d_active.p;
   a.pose = S->d_pose[S->cur].p; a.K = S->d_K[S->cur].p;
   a.pose_c = S->d_pose[1 - S->cur].p; a.K_c = S->d_K[1 - S->cur].p;
-  a.F = S->F; a.C = S->C; a.acc = S->d_rep.p;
+  a.F = S->F; a.C = S->C; a.acc = S->d_step.p + 4;
   const int n = S->F + S->C;
   k_apply_cams<<<(n + 255) / 256, 256, 0, S->stream>>>(a);
   PSFM_LAUNCH_CHECK();
@@ -1394,8 +1392,7 @@ StepOut compute_step(psfm_ba_solver* S, const RunCfg& c, double radius, int* npr
     PSFM_LAUNCH_CHECK();
   }
   dist::allreduce_sum(S->d_step.p, 4, S->stream);
-  d2h(S, S->hs->step, S->d_step.p, 4);
-  d2h(S, S->hs->rep, S->d_rep.p, 2);
+  d2h(S, S->hs->step, S->d_step.p, 6);          // step[4] | rep[2]: adjacent in HostScalars and in d_step
   d2h(S, &S->hs->prep_fail, S->d_prep.p + (size_t)S->F * NVL + (size_t)S->C * NVI, 1);
   if (explicit_ok) d2h(S, &S->hs->chol_fail, S->d_cholfail.p, 1);
   PSFM_CUDA(cudaStreamSynchronize(S->stream));

@@ -63,10 +63,10 @@ int rank() { return g.rank; }
 // The collectives of an LM iteration are tiny (4 doubles ... 0.8 MB) and latency-bound: NCCL costs
 // 15-30 us per call at 8 ranks.  On one NVSwitch node every rank can LOAD every peer's buffer directly:
 // each rank owns a symmetric buffer (cudaMalloc, exported with cudaIpcGetMemHandle, the handles exchanged
-// once through the NCCL communicator) and a flag array.  k_p2p_publish copies the local operand into the
+// once through the NCCL communicator) and a flag array.  k_p2p_allreduce copies the local operand into the
 // rank's symmetric buffer (parity = epoch & 1) and, when the last CTA is done, stores the epoch into
-// flags[my_rank] of EVERY peer (system-scope release over NVLink).  k_p2p_reduce waits until all its own
-// flags reach the epoch (acquire), then every rank sums (or max-es) the world's buffers in rank order —
+// flags[my_rank] of EVERY peer (system-scope release over NVLink); it then waits until all its own
+// flags reach the epoch (acquire) and every rank sums (or max-es) the world's buffers in rank order —
 // the same order on every rank, so the replicated results are bit-identical across ranks — and writes
 // the result over the local operand.  Two parities make the buffer of epoch k safe to overwrite in epoch
 // k+2: passing the barrier of epoch k+1 means every peer has finished reading epoch k.  A wait that
@@ -90,9 +90,17 @@ struct P2PPtrs {
   unsigned long long* flags[P2P_MAX_WORLD];
 };
 
-__global__ void __launch_bounds__(256) k_p2p_publish(const double* __restrict__ src, size_t n, double* __restrict__ dst, P2PPtrs pp,
-                                                     int me, int world, unsigned long long epoch, unsigned long long* counter) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+// ONE kernel per all-reduce (a launch costs as much as the whole exchange at this size): every block copies its share
+// of the operand into the symmetric buffer; the block that finishes last raises this rank's flag on every peer
+// (system-scope release over NVLink); then every block waits until all ranks — its own included, so the in-place
+// result never overwrites an operand a sibling block is still copying — have raised theirs, and reduces in rank order.
+// The grid (P2P_GRID blocks) is far below one wave, so the spinning blocks cannot starve the publishing ones.
+constexpr int P2P_GRID = 32;
+__global__ void __launch_bounds__(256) k_p2p_allreduce(double* __restrict__ buf, size_t n, size_t parity_off, P2PPtrs pp, int me, int world,
+                                                       unsigned long long epoch, int op_max, unsigned long long* counter,
+                                                       unsigned long long* err) {
+  double* dst = pp.sym[me] + parity_off;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = buf[i];
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
@@ -103,10 +111,6 @@ __global__ void __launch_bounds__(256) k_p2p_publish(const double* __restrict__ 
     unsigned long long* f = pp.flags[threadIdx.x] + me;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
   }
-}
-
-__global__ void __launch_bounds__(256) k_p2p_reduce(double* __restrict__ out, size_t n, size_t parity_off, P2PPtrs pp, int me, int world,
-                                                    unsigned long long epoch, int op_max, unsigned long long* err) {
   if (threadIdx.x < world) {
     const unsigned long long* f = pp.flags[me] + threadIdx.x;
     unsigned long long v = 0;
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(256) k_p2p_reduce(double* __restrict__ out, si
       const double v = __ldcg(pp.sym[r] + parity_off + i);
       acc = op_max ? fmax(acc, v) : acc + v;
     }
-    out[i] = acc;
+    buf[i] = acc;
   }
 }
 
@@ -187,12 +191,9 @@ static bool p2p_allreduce(double* buf, size_t n, int op_max, cudaStream_t stream
   const size_t off = (epoch & 1) * (P2P_BYTES / sizeof(double));
   P2PPtrs pp;
   for (int r = 0; r < P2P_MAX_WORLD; ++r) { pp.sym[r] = p2p.sym[r]; pp.flags[r] = p2p.flags[r]; }
-  // fixed grid: the publish counter advances by PUB_GRID per epoch on every call
-  constexpr int PUB_GRID = 32;
-  k_p2p_publish<<<PUB_GRID, 256, 0, stream>>>(buf, n, p2p.sym_local + off, pp, g.rank, g.world, epoch, p2p.flags_local + P2P_MAX_WORLD);
-  g_launch_count.fetch_add(1);
-  const int rgrid = (int)std::min<size_t>(64, (n + 255) / 256);
-  k_p2p_reduce<<<rgrid < 1 ? 1 : rgrid, 256, 0, stream>>>(buf, n, off, pp, g.rank, g.world, epoch, op_max, p2p.flags_local + P2P_MAX_WORLD + 1);
+  // fixed grid: the publish counter advances by P2P_GRID per epoch on every call
+  k_p2p_allreduce<<<P2P_GRID, 256, 0, stream>>>(buf, n, off, pp, g.rank, g.world, epoch, op_max, p2p.flags_local + P2P_MAX_WORLD,
+                                                p2p.flags_local + P2P_MAX_WORLD + 1);
   g_launch_count.fetch_add(1);
   return cudaGetLastError() == cudaSuccess;
 }
