@@ -63,3 +63,20 @@ def test_no_cpu_fallback():
     _lib.lib().psfm_ba_global_options(C.byref(o))
     with pytest.raises(_lib.PsfmError, match="no CUDA device"):
         ba.solve_problem(prob, o)
+
+
+@pytest.mark.skipif(_lib.lib().psfm_device_count() > 0, reason="needs a machine WITHOUT a GPU")
+def test_no_cpu_fallback_of_the_initialisation_ops():
+    """SURVEY.md 8(f) f-4 ops: host-side argument checks come first, then the library refuses without a device."""
+    import numpy as np
+    from particlesfm_b200 import init_geometry as ig
+    p = np.zeros((5, 2))
+    q = np.array([1.0, 0.0, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        ig.batch_optimize_relative_position_with_known_rotation([(p, p[:-1], q, q)])
+    with pytest.raises(_lib.PsfmError, match="no CUDA device"):
+        ig.optimize_relative_position_with_known_rotation(p, p, q, q)
+    with pytest.raises(_lib.PsfmError, match="no CUDA device"):
+        ig.triangulate_multi_view_points([(np.zeros((2, 3, 4)), np.zeros((2, 2)))])
+    assert ig.batch_optimize_relative_position_with_known_rotation([]).shape == (0, 3)      # nothing to do: no device needed
+    assert ig.triangulate_multi_view_points([]).shape == (0, 3)
