@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_band_chol(const BandCholArgs a) {
   double* colbuf = bc_smem;                 // [2][BC_CSM]   pivot column by window position (double buffered)
   double* ring = colbuf + 2 * BC_CSM;       // [BC_RING][BC_CSM] upcoming rows, permuted to window positions
   double* stage = ring + BC_RING * BC_CSM;  // [2][32][LSP] coefficients of the back substitution
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int NT = (Wb + 1) * (Wb + 2) / 2;
   const int ldr0 = (NT + 31) & ~31;         // first helper thread; blockDim.x = ldr0 + 32 * ceil((W + 4) / 32)
   const bool worker = tid < NT, helper = tid >= ldr0;

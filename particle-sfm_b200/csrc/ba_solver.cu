@@ -1523,7 +1523,7 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
   double x_norm = std::sqrt(current_x_sqnorm(S));
   s.initial_cost = x_cost;
   int term = PSFM_TERM_NO_CONVERGENCE;
-  bool step_ok_prev = true, points_ready = true;
+  bool step_ok_prev = true;
   if (o.minimizer_progress_to_stdout)
     printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter\n%4d % .6e  % .3e  % .3e\n",
            0, x_cost, 0.0, gmax);
@@ -1534,7 +1534,6 @@ int run_impl(psfm_ba_solver* S, const psfm_ba_options* opts, psfm_ba_summary* ou
     if (radius <= o.min_trust_region_radius) { term = PSFM_TERM_MIN_RADIUS; break; }
     ++iteration;
     step_ok_prev = false;
-    (void)points_ready;
     const StepOut so = compute_step(S, c, radius, &nprod);
     s.num_linear_iterations += so.pcg_iters;
     const bool valid = so.linear_ok && so.mcc > 0.0;
